@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference interfaces for the vpsi / rhoofr path.
+
+Two levels:
+
+* :class:`Plan` — thin object over the C ABI (``include/cpb200.h``): host-array entry points
+  (what the Fortran shim binds) and device-pointer entry points (torch CUDA tensors).
+* :class:`CpmdContext` — mirrors the *reference's own call signatures*: the reference keeps mesh,
+  G-vector and occupation data in module globals (``spar``, ``fpar``, ``ncpw``, ``cppt``, ``parm``,
+  ``crge``, ``parai``) and calls ``rhoofr(c0,rhoe,psi,nstate)`` (rhoofr_utils.mod.F90:122) and
+  ``vpsi(c0,c2,f,vpot,psi,nstate,ikind,ispin,redist_c2)`` (vpsi_utils.mod.F90:120); the context
+  holds those globals and exposes methods with exactly those argument lists.  Unsupported
+  variants raise :class:`StopGM` like the reference's ``stopgm``.
+
+Array conventions: a Fortran array ``c0(ld, nstate)`` is a C-contiguous numpy/torch array of
+shape ``(nstate, ld)``; ``rhoe``/``vpot`` ``(nnr1[, nspin])`` are flat float64 arrays of length
+``kr1*kr2s*kr3s`` (x fastest).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class CpbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cpb200 error {code}: {msg}")
+        self.code = code
+
+
+class StopGM(RuntimeError):
+    """Python stand-in for ``CALL stopgm(procedure, message, __LINE__, __FILE__)``
+    (error_handling.mod.F90:11-53): the reference's only error convention is to abort."""
+
+    def __init__(self, procedure, message):
+        super().__init__(f"{procedure}: {message}")
+        self.procedure = procedure
+        self.message = message
+
+
+def leadim(nr: int) -> int:
+    """kr = nr + MOD(nr+1, 2) (loadpa_utils.mod.F90:509-525)."""
+    return nr + (nr + 1) % 2
+
+
+def _ptr(a):
+    """Raw address of a numpy array or torch tensor (None -> NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch
+
+
+def _is_torch(a):
+    return not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
+
+
+class Plan:
+    """One FFT/G-vector plan on one GPU (``cpb_plan_create``)."""
+
+    def __init__(self, nr, inyh, hg, tpiba2=1.0, omega=1.0, kr=None, device=0, max_batch=16, _cdll=None):
+        self._L = _cdll if _cdll is not None else _lib.load()
+        self._h = C.c_void_p()
+        nr = tuple(int(v) for v in nr)
+        kr = tuple(leadim(v) for v in nr) if kr is None else tuple(int(v) for v in kr)
+        inyh = np.asarray(inyh)
+        if inyh.ndim != 2 or inyh.shape[0] != 3:
+            raise ValueError("inyh must have shape (3, ngw) like the Fortran array")
+        ngw = inyh.shape[1]
+        inyh_f = np.ascontiguousarray(inyh.T, dtype=np.int32)  # (ngw,3) C-order == (3,ngw) Fortran
+        hg = np.ascontiguousarray(hg, dtype=np.float64)
+        if hg.shape != (ngw,):
+            raise ValueError("hg must have shape (ngw,)")
+        nr_c = (C.c_int * 3)(*nr)
+        kr_c = (C.c_int * 3)(*kr)
+        rc = self._L.cpb_plan_create(C.byref(self._h), nr_c, kr_c, ngw, inyh_f.ctypes.data, hg.ctypes.data,
+                                     float(tpiba2), float(omega), int(device), int(max_batch))
+        self._check(rc)
+        self.nr, self.kr, self.ngw = nr, kr, ngw
+        self.tpiba2, self.omega, self.device = float(tpiba2), float(omega), int(device)
+        self.nnr1 = kr[0] * kr[1] * kr[2]
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise CpbError(rc, self._L.cpb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.cpb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self):
+        inf = _lib.PlanInfo()
+        self._check(self._L.cpb_plan_get_info(self._h, C.byref(inf)))
+        return dict(nr=tuple(inf.nr), kr=tuple(inf.kr), ngw=inf.ngw, geq0=bool(inf.geq0), nrays=inf.nrays,
+                    zband=inf.zband, xband=inf.xband, max_batch=inf.max_batch, device=inf.device,
+                    radix=tuple((inf.radix[d][0], inf.radix[d][1]) for d in range(3)),
+                    workspace_bytes=inf.workspace_bytes)
+
+    def maps(self):
+        """(nzhs, indzs) with the reference's numbering (fftprp_utils.mod.F90:269-285)."""
+        nzhs = np.empty(self.ngw, dtype=np.int32)
+        indzs = np.empty(self.ngw, dtype=np.int32)
+        self._check(self._L.cpb_plan_get_maps(self._h, nzhs.ctypes.data, indzs.ctypes.data))
+        return nzhs, indzs
+
+    @property
+    def launch_count(self):
+        return int(self._L.cpb_plan_launch_count(self._h))
+
+    def _c0_args(self, c0, nstate):
+        if c0.ndim != 2:
+            raise ValueError("c0 must be (nstate, ld)")
+        ns, ld = c0.shape
+        if nstate is None:
+            nstate = ns
+        if nstate > ns or ld < self.ngw:
+            raise ValueError("c0 shape inconsistent with nstate/ngw")
+        return int(nstate), int(ld)
+
+    # -- host-array entry points (the Fortran drop-in path) --------------------------------
+    def rhoofr(self, c0, f, rhoe=None, nstate=None, ngroups=1, my_group=0, flags=0):
+        """``cpb_rhoofr``: c0 (nstate, ld) complex128 numpy (host).  Returns
+        (rhoe, ekin, rsum_g, rsum_r); rhoe is written into the given array if supplied."""
+        c0 = _as_host(c0, np.complex128)
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if rhoe is None:
+            rhoe = np.empty(self.nnr1, dtype=np.float64)
+        rh = _as_host(rhoe, np.float64)
+        if rh.size < self.nnr1:
+            raise ValueError("rhoe too small")
+        ekin, rg, rr = C.c_double(), C.c_double(), C.c_double()
+        rc = self._L.cpb_rhoofr(self._h, c0.ctypes.data, ld, nstate, f.ctypes.data, ngroups, my_group,
+                                rh.ctypes.data, C.byref(ekin), C.byref(rg), C.byref(rr), flags)
+        self._check(rc)
+        return rhoe, ekin.value, rg.value, rr.value
+
+    def vpsi(self, c0, c2, f, vpot, nstate=None, ngroups=1, my_group=0, flags=0):
+        """``cpb_vpsi``: c2 (host, in/out) is accumulated into unless CPB_VPSI_OVERWRITE."""
+        c0 = _as_host(c0, np.complex128)
+        c2h = _as_host(c2, np.complex128)
+        if c2h.shape != c0.shape:
+            raise ValueError("c2 must have the shape of c0")
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        v = _as_host(vpot, np.float64)
+        if v.size < self.nnr1:
+            raise ValueError("vpot too small")
+        rc = self._L.cpb_vpsi(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data,
+                              v.ctypes.data, ngroups, my_group, flags)
+        self._check(rc)
+        return c2
+
+    def c0_upload(self, c0, nstate=None, ngroups=1, my_group=0):
+        c0 = _as_host(c0, np.complex128)
+        nstate, ld = self._c0_args(c0, nstate)
+        self._check(self._L.cpb_c0_upload(self._h, c0.ctypes.data, ld, nstate, ngroups, my_group))
+
+    def c0_invalidate(self):
+        self._check(self._L.cpb_c0_invalidate(self._h))
+
+    # -- device-pointer entry points (torch CUDA tensors) ----------------------------------
+    def rhoofr_dev(self, c0, f, rhoe, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
+        """``cpb_rhoofr_dev``: c0 (nstate, ld) complex128 CUDA tensor, rhoe float64 CUDA tensor of
+        nnr1 elements (overwritten).  Returns (ekin, rsum_g, rsum_r) of the group's block."""
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if rhoe.numel() < self.nnr1:
+            raise ValueError("rhoe too small")
+        ekin, rg, rr = C.c_double(), C.c_double(), C.c_double()
+        rc = self._L.cpb_rhoofr_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, ngroups, my_group,
+                                    _ptr(rhoe), C.byref(ekin), C.byref(rg), C.byref(rr), flags,
+                                    _stream_ptr(stream))
+        self._check(rc)
+        return ekin.value, rg.value, rr.value
+
+    def vpsi_dev(self, c0, c2, f, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        rc = self._L.cpb_vpsi_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, _ptr(vpot),
+                                  ngroups, my_group, flags, _stream_ptr(stream))
+        self._check(rc)
+        return c2
+
+
+def _as_host(a, dtype):
+    """numpy view of a host array (numpy, or a CPU/pinned torch tensor) without copying."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != dtype or not a.flags.c_contiguous:
+            raise ValueError(f"expected a C-contiguous {np.dtype(dtype).name} array")
+        return a
+    if _is_torch(a):
+        if a.is_cuda:
+            raise ValueError("host entry point called with a CUDA tensor; use the *_dev variant")
+        return a.numpy()
+    raise TypeError("expected numpy array or torch tensor")
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        except Exception:
+            pass
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# mirror of the reference's module-global state + subroutine signatures
+# ---------------------------------------------------------------------------------------------
+
+@dataclass
+class CpmdContext:
+    """The module globals the two subroutines read, gathered in one object.
+
+    spar%nr1s.. -> ``nr``; fpar%kr1.. -> ``kr``; ncpw%ngw -> ``ngw``; cppt inyh/hg; parm%tpiba2,
+    parm%omega; crge%f(:,1) -> ``f`` (rhoofr's occupations); parai%cp_nogrp / cp_inter_me ->
+    ``cp_nogrp`` / ``cp_inter_me``; the variant flags that the GPU path does not implement.
+    """
+    nr: tuple
+    inyh: np.ndarray
+    hg: np.ndarray
+    tpiba2: float = 1.0
+    omega: float = 1.0
+    f: np.ndarray = None              # crge%f(:,1)
+    cp_nogrp: int = 1                 # parai%cp_nogrp
+    cp_inter_me: int = 0              # parai%cp_inter_me
+    device: int = 0
+    max_batch: int = 16
+    # variant switches (must all be off; otherwise the shim falls back to the original routine)
+    tkpnt: bool = False               # tkpts%tkpnt
+    tlsd: bool = False                # cntl%tlsd
+    tlse: bool = False                # lspin2%tlse
+    ttau: bool = False                # cntl%ttau
+    tdg: bool = False                 # tdgcomm%tdg
+    rsactive: bool = False
+    tksham: bool = False              # cntl%tksham
+    akin: float = 0.0                 # prcp_com%akin
+    nogrp: int = 1                    # group%nogrp (old task groups)
+    delta: float = 1.0e-6             # rhoofr charge tolerance (rhoofr_utils.mod.F90:141)
+    plan: Plan = field(default=None, repr=False)
+    _cdll: object = field(default=None, repr=False)
+    # outputs the reference stores in globals
+    ekin: float = 0.0                 # ener_com%ekin
+    csumg: float = 0.0                # chrg%csumg
+    csumr: float = 0.0                # chrg%csumr
+
+    def __post_init__(self):
+        if self.plan is None:
+            self.plan = Plan(self.nr, self.inyh, self.hg, self.tpiba2, self.omega, device=self.device,
+                             max_batch=self.max_batch, _cdll=self._cdll)
+        self.kr = self.plan.kr
+        self.ngw = self.plan.ngw
+        self.nnr1 = self.plan.nnr1
+
+    def _check_variant(self, proc):
+        if self.nogrp > 1:
+            raise StopGM(proc, "OLD TASK GROUPS NOT SUPPORTED ANYMORE ")  # vpsi_utils.mod.F90:173-175
+        for flag, name in ((self.tkpnt, "k-points"), (self.tlsd, "LSD"), (self.tlse, "LSE"),
+                           (self.ttau, "meta-GGA tau"), (self.tdg, "double grid"),
+                           (self.rsactive, "REAL SPACE WFN KEEP"), (self.akin > 1.0e-10, "AKIN")):
+            if flag:
+                raise StopGM(proc, f"{name} variant is not implemented on the GPU path")
+
+    def rhoofr(self, c0, rhoe, psi, nstate):
+        """``SUBROUTINE rhoofr(c0,rhoe,psi,nstate)`` (rhoofr_utils.mod.F90:122-137).
+        ``psi`` is the caller's scratch array; unused (the library owns its work space).
+        Sets ``ekin``, ``csumg``, ``csumr`` like the reference sets ener_com%ekin, chrg%csum*.
+        With cp_nogrp > 1 ``rhoe``/sums are the group's partial results: the caller performs
+        cp_grp_redist (see cpmd_b200.dist)."""
+        proc = "rhoofr"
+        self._check_variant(proc)
+        if self.f is None:
+            raise StopGM(proc, "occupation numbers crge%f not set")
+        dev = _is_torch(c0) and c0.is_cuda
+        rh = rhoe if rhoe.ndim == 1 else rhoe.reshape(-1)
+        if dev:
+            ekin, rg, rr = self.plan.rhoofr_dev(c0, self.f, rh, nstate, self.cp_nogrp, self.cp_inter_me)
+        else:
+            _, ekin, rg, rr = self.plan.rhoofr(c0, self.f, rh, nstate, self.cp_nogrp, self.cp_inter_me)
+        self.ekin, self.csumg, self.csumr = ekin, rg, rr
+        if self.cp_nogrp == 1 and abs(rr - rg) > self.delta:
+            raise StopGM(proc, "TOTAL DENSITY SUMS ARE NOT EQUAL")  # :625-635
+
+    def vpsi(self, c0, c2, f, vpot, psi, nstate, ikind=1, ispin=1, redist_c2=False):
+        """``SUBROUTINE vpsi(c0,c2,f,vpot,psi,nstate,ikind,ispin,redist_c2)``
+        (vpsi_utils.mod.F90:120-135).  c2 += -(f/2) [tpiba2 hg c0 + 2 FFT(V psi)] for the
+        group's states.  ``redist_c2`` is the caller's job here (cpmd_b200.dist.redist_c2)."""
+        proc = "vpsi"
+        self._check_variant(proc)
+        if ikind != 1:
+            raise StopGM(proc, "k-points (ikind>1) not implemented on the GPU path")
+        if ispin != 1:
+            raise StopGM(proc, "LSD (ispin=2) not implemented on the GPU path")
+        flags = _lib.CPB_VPSI_TKSHAM if self.tksham else 0
+        v = vpot if vpot.ndim == 1 else vpot.reshape(-1)
+        if _is_torch(c0) and c0.is_cuda:
+            self.plan.vpsi_dev(c0, c2, f, v, nstate, self.cp_nogrp, self.cp_inter_me, flags)
+        else:
+            self.plan.vpsi(c0, c2, f, v, nstate, self.cp_nogrp, self.cp_inter_me, flags)

@@ -1,0 +1,173 @@
+// In-register DFT codelets, FP64, natural-order in/out, fully unrolled at compile time.
+//
+// dft<R, INV>(v):  v[p] <- sum_k v[k] * w^(k p),  w = exp(-2 pi i / R)  (INV = false, "forward",
+// CPMD isign=+1, mltfft_utils.mod.F90:514-518) or exp(+2 pi i / R) (INV = true, "inverse",
+// isign=-1).  No scaling.
+//
+// Supported radices: 2,3,4,5,7 (direct butterflies) and the composites listed in Split<>
+// (Cooley-Tukey in registers with literal twiddles from roots.h; trivial twiddles cost nothing).
+// This plays the role of the reference's radix-3/4/5/6/8 passes (gfft_utils.mod.F90:136-3412)
+// but is a different algorithm: the reference runs Stockham passes over a cache-blocked batch in
+// memory; here one thread owns a whole radix-R sub-transform in registers.
+#pragma once
+#include "cpb_defs.h"
+#include "roots.h"
+
+namespace cpb {
+
+// multiply by exp(-/+ 2 pi i K / DEN)
+template <int DEN, int K, bool INV>
+CPB_HD cplx mul_root(cplx a) {
+  constexpr int k = ((K % DEN) + DEN) % DEN;
+  if constexpr (k == 0) {
+    return a;
+  } else if constexpr (2 * k == DEN) {
+    return mk(-a.x, -a.y);
+  } else if constexpr (4 * k == DEN) {
+    // forward: * (-i) ; inverse: * (+i)
+    return INV ? mk(-a.y, a.x) : mk(a.y, -a.x);
+  } else if constexpr (4 * k == 3 * DEN) {
+    return INV ? mk(a.y, -a.x) : mk(-a.y, a.x);
+  } else {
+    constexpr double c = Root<DEN>::c(k);
+    constexpr double s = INV ? Root<DEN>::s(k) : -Root<DEN>::s(k);
+    return mk(a.x * c - a.y * s, a.x * s + a.y * c);
+  }
+}
+
+template <int R>
+struct Split {
+  static constexpr int a = 1;  // 1 => prime / direct butterfly
+};
+#define CPB_SPLIT(R, A) \
+  template <>           \
+  struct Split<R> {     \
+    static constexpr int a = A; \
+  };
+CPB_SPLIT(6, 2)
+CPB_SPLIT(8, 2)
+CPB_SPLIT(9, 3)
+CPB_SPLIT(10, 2)
+CPB_SPLIT(12, 4)
+CPB_SPLIT(14, 2)
+CPB_SPLIT(15, 3)
+CPB_SPLIT(16, 4)
+CPB_SPLIT(18, 2)
+CPB_SPLIT(20, 4)
+CPB_SPLIT(21, 3)
+CPB_SPLIT(24, 4)
+CPB_SPLIT(25, 5)
+CPB_SPLIT(28, 4)
+CPB_SPLIT(30, 5)
+CPB_SPLIT(32, 4)
+#undef CPB_SPLIT
+
+template <int R, bool INV>
+CPB_HD void dft(cplx (&v)[R]);
+
+// odd prime P: pair up k and P-k
+template <int P, bool INV>
+CPB_HD void dft_prime(cplx (&v)[P]) {
+  constexpr int H = (P - 1) / 2;
+  cplx s[H + 1], d[H + 1];
+  static_for<1, H + 1>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    s[j] = cadd(v[j], v[P - j]);
+    d[j] = csub(v[j], v[P - j]);
+  });
+  cplx v0 = v[0];
+  cplx sum = v0;
+  static_for<1, H + 1>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    sum = cadd(sum, s[j]);
+  });
+  v[0] = sum;
+  static_for<1, H + 1>([&](auto kk) {
+    constexpr int k = decltype(kk)::value;
+    cplx A = v0;
+    cplx Bv = mk(0.0, 0.0);
+    static_for<1, H + 1>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      constexpr double c = Root<P>::c((j * k) % P);
+      constexpr double sn = Root<P>::s((j * k) % P);
+      A.x += c * s[j].x;
+      A.y += c * s[j].y;
+      if constexpr (j == 1) {
+        Bv.x = sn * d[j].x;
+        Bv.y = sn * d[j].y;
+      } else {
+        Bv.x += sn * d[j].x;
+        Bv.y += sn * d[j].y;
+      }
+    });
+    // forward: X_k = A - i B, X_{P-k} = A + i B ; inverse: swapped
+    cplx mib = mk(Bv.y, -Bv.x);  // -i * B
+    if (INV) {
+      v[k] = csub(A, mib);
+      v[P - k] = cadd(A, mib);
+    } else {
+      v[k] = cadd(A, mib);
+      v[P - k] = csub(A, mib);
+    }
+  });
+}
+
+template <bool INV>
+CPB_HD void dft4(cplx (&v)[4]) {
+  cplx t0 = cadd(v[0], v[2]);
+  cplx t1 = csub(v[0], v[2]);
+  cplx t2 = cadd(v[1], v[3]);
+  cplx t3 = mul_root<4, 1, INV>(csub(v[1], v[3]));
+  v[0] = cadd(t0, t2);
+  v[1] = cadd(t1, t3);
+  v[2] = csub(t0, t2);
+  v[3] = csub(t1, t3);
+}
+
+template <int R, bool INV>
+CPB_HD void dft(cplx (&v)[R]) {
+  if constexpr (R == 1) {
+  } else if constexpr (R == 2) {
+    cplx a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else if constexpr (R == 4) {
+    dft4<INV>(v);
+  } else if constexpr (Split<R>::a == 1) {
+    static_assert(R == 3 || R == 5 || R == 7, "unsupported prime radix");
+    dft_prime<R, INV>(v);
+  } else {
+    // Cooley-Tukey R = Ra * Rb: index k = j + Rb*ka, output p + Ra*q
+    constexpr int Ra = Split<R>::a;
+    constexpr int Rb = R / Ra;
+    cplx t[R];
+    static_for<0, Rb>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      cplx u[Ra];
+      static_for<0, Ra>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        u[k] = v[j + Rb * k];
+      });
+      dft<Ra, INV>(u);
+      static_for<0, Ra>([&](auto pp) {
+        constexpr int p = decltype(pp)::value;
+        t[j * Ra + p] = mul_root<R, j * p, INV>(u[p]);
+      });
+    });
+    static_for<0, Ra>([&](auto pp) {
+      constexpr int p = decltype(pp)::value;
+      cplx u[Rb];
+      static_for<0, Rb>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        u[j] = t[j * Ra + p];
+      });
+      dft<Rb, INV>(u);
+      static_for<0, Rb>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        v[p + Ra * q] = u[q];
+      });
+    });
+  }
+}
+
+}  // namespace cpb

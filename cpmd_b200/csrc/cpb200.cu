@@ -1,0 +1,733 @@
+// cpb200: plan construction (host side of fftprp/loadpa-derived index maps) and the C ABI.
+// See include/cpb200.h for the contract and the reference file:line each entry point replaces.
+#include "../../include/cpb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "axis.h"
+#include "misc_kernels.h"
+#include "rt.h"
+
+using namespace cpb;
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+template <class T>
+T* upload(const std::vector<T>& h) {
+  T* d = (T*)rt::dmalloc(h.size() * sizeof(T));
+  if (!h.empty()) {
+    rt::h2d(d, h.data(), h.size() * sizeof(T), 0);
+    rt::sync(0);
+  }
+  return d;
+}
+
+struct PairHost {
+  int s1, s2;  // 0-based global state indices, s2 = -1 for a trailing single state
+};
+
+// part_1d.mod.F90:22-57
+int nbr_el_in_blk(int n_elem, int proc, int nproc) {
+  const int res = n_elem % nproc;
+  int nbr = (n_elem - res) / nproc;
+  if (proc < res) nbr += 1;
+  return nbr;
+}
+int get_el_in_blk(int i_elem, int n_elem, int proc, int nproc) {
+  const int res = n_elem % nproc;
+  const int nbr = (n_elem - res) / nproc;
+  return i_elem + nbr * proc + std::min(proc, res);
+}
+
+// pairs formed inside the group's block: vpsi_utils.mod.F90:376-383, rhoofr_utils.mod.F90:306-310
+std::vector<PairHost> block_pairs(int nstate, int my_group, int ngroups) {
+  std::vector<PairHost> out;
+  const int nblk = nbr_el_in_blk(nstate, my_group, ngroups);
+  for (int i = 1; i <= nblk; i += 2) {
+    PairHost p;
+    p.s1 = get_el_in_blk(i, nstate, my_group, ngroups) - 1;
+    p.s2 = (i + 1 <= nblk) ? get_el_in_blk(i + 1, nstate, my_group, ngroups) - 1 : -1;
+    out.push_back(p);
+  }
+  return out;
+}
+}  // namespace
+
+struct cpb_plan {
+  int nr[3], kr[3];
+  int ngw = 0;
+  int geq0 = 0;
+  double tpiba2 = 0, omega = 0;
+  int device = 0;
+  int max_batch = 16;
+  const AxisKernels *kx = nullptr, *ky = nullptr, *kz = nullptr;
+  // geometry (host copies)
+  int xlo = 0, xhi = -1, zlo = 0, nzb = 0, nrays = 0, ref_nrays = 0, ntiles = 0, nent = 0;
+  std::vector<int32_t> nzhs, indzs;
+  // device data
+  PlanDev pd;
+  int *d_ylo = nullptr, *d_yhi = nullptr, *d_rayoff = nullptr, *d_slot_ray = nullptr,
+      *d_ent_off = nullptr, *d_ent_ig = nullptr;
+  uint32_t* d_ent_loc = nullptr;
+  double* d_hg = nullptr;
+  cplx *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw3 = nullptr;
+  cplx *T1 = nullptr, *T2 = nullptr;
+  size_t workspace_bytes = 0;
+  // per-call pair descriptors
+  int pair_cap = 0;
+  int *d_st1 = nullptr, *d_st2 = nullptr;
+  double *d_ca = nullptr, *d_cb = nullptr;
+  void* h_pairs = nullptr;  // pinned staging for the four arrays
+  // reductions
+  int red_cap = 0;
+  double* d_red = nullptr;
+  double* h_red = nullptr;  // pinned
+  // host-pointer API staging
+  cplx* d_c0 = nullptr;
+  size_t d_c0_cap = 0;
+  cplx* d_c2 = nullptr;
+  size_t d_c2_cap = 0;
+  double* d_real = nullptr;  // rho or V, nnr1
+  cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
+  std::vector<rt::event_t> ev_in, ev_done;
+  // c0 cache key
+  const void* c0_key_ptr = nullptr;
+  long c0_key_ld = 0;
+  int c0_key_nstate = 0, c0_key_ngroups = 0, c0_key_group = 0;
+  bool c0_valid = false;
+  long launches = 0;
+
+  size_t nnr1() const { return (size_t)kr[0] * kr[1] * kr[2]; }
+};
+
+namespace {
+
+void free_plan(cpb_plan* p) {
+  if (!p) return;
+  rt::dfree(p->d_ylo);
+  rt::dfree(p->d_yhi);
+  rt::dfree(p->d_rayoff);
+  rt::dfree(p->d_slot_ray);
+  rt::dfree(p->d_ent_off);
+  rt::dfree(p->d_ent_ig);
+  rt::dfree(p->d_ent_loc);
+  rt::dfree(p->d_hg);
+  rt::dfree(p->d_tw1);
+  rt::dfree(p->d_tw2);
+  rt::dfree(p->d_tw3);
+  rt::dfree(p->T1);
+  rt::dfree(p->T2);
+  rt::dfree(p->d_st1);
+  rt::dfree(p->d_st2);
+  rt::dfree(p->d_ca);
+  rt::dfree(p->d_cb);
+  rt::hfree_pinned(p->h_pairs);
+  rt::dfree(p->d_red);
+  rt::hfree_pinned(p->h_red);
+  rt::dfree(p->d_c0);
+  rt::dfree(p->d_c2);
+  rt::dfree(p->d_real);
+  for (auto e : p->ev_in) rt::event_destroy(e);
+  for (auto e : p->ev_done) rt::event_destroy(e);
+  rt::stream_destroy(p->s_main);
+  rt::stream_destroy(p->s_in);
+  rt::stream_destroy(p->s_out);
+  delete p;
+}
+
+std::vector<cplx> make_twiddles(int n) {
+  std::vector<cplx> tw(n);
+  const long double twopi = 6.283185307179586476925286766559005768L;
+  for (int m = 0; m < n; ++m) {
+    // exact octant values first, so trivial twiddles are exact
+    if ((8 * m) % n == 0) {
+      static const double c8[8] = {1, M_SQRT1_2, 0, -M_SQRT1_2, -1, -M_SQRT1_2, 0, M_SQRT1_2};
+      static const double s8[8] = {0, M_SQRT1_2, 1, M_SQRT1_2, 0, -M_SQRT1_2, -1, -M_SQRT1_2};
+      const int o = (8 * m) / n;
+      tw[m] = mk(c8[o], s8[o]);
+    } else {
+      const long double a = twopi * (long double)m / (long double)n;
+      tw[m] = mk((double)cosl(a), (double)sinl(a));
+    }
+  }
+  return tw;
+}
+
+void ensure_pairs(cpb_plan* p, int npairs) {
+  if (npairs <= p->pair_cap) return;
+  const int cap = std::max(npairs, 2 * p->pair_cap);
+  rt::dfree(p->d_st1);
+  rt::dfree(p->d_st2);
+  rt::dfree(p->d_ca);
+  rt::dfree(p->d_cb);
+  rt::hfree_pinned(p->h_pairs);
+  p->d_st1 = (int*)rt::dmalloc(cap * sizeof(int));
+  p->d_st2 = (int*)rt::dmalloc(cap * sizeof(int));
+  p->d_ca = (double*)rt::dmalloc(cap * sizeof(double));
+  p->d_cb = (double*)rt::dmalloc(cap * sizeof(double));
+  p->h_pairs = rt::hmalloc_pinned((size_t)cap * (2 * sizeof(int) + 2 * sizeof(double)));
+  p->pair_cap = cap;
+}
+
+void ensure_red(cpb_plan* p, int n) {
+  if (n <= p->red_cap) return;
+  rt::dfree(p->d_red);
+  rt::hfree_pinned(p->h_red);
+  p->d_red = (double*)rt::dmalloc((size_t)n * sizeof(double));
+  p->h_red = (double*)rt::hmalloc_pinned((size_t)n * sizeof(double));
+  p->red_cap = n;
+}
+
+// stage the per-pair descriptors of one call; returns base PairDev
+PairDev upload_pairs(cpb_plan* p, const std::vector<PairHost>& pairs, const std::vector<double>& ca,
+                     const std::vector<double>& cb, cudaStream_t st) {
+  const int np = (int)pairs.size();
+  ensure_pairs(p, np);
+  double* hca = (double*)p->h_pairs;
+  double* hcb = hca + p->pair_cap;
+  int* hs1 = (int*)(hcb + p->pair_cap);
+  int* hs2 = hs1 + p->pair_cap;
+  for (int i = 0; i < np; ++i) {
+    hs1[i] = pairs[i].s1;
+    hs2[i] = pairs[i].s2;
+    hca[i] = ca[i];
+    hcb[i] = cb[i];
+  }
+  if (np) {
+    rt::h2d(p->d_st1, hs1, np * sizeof(int), st);
+    rt::h2d(p->d_st2, hs2, np * sizeof(int), st);
+    rt::h2d(p->d_ca, hca, np * sizeof(double), st);
+    rt::h2d(p->d_cb, hcb, np * sizeof(double), st);
+  }
+  PairDev pr;
+  pr.st1 = p->d_st1;
+  pr.st2 = p->d_st2;
+  pr.ca = p->d_ca;
+  pr.cb = p->d_cb;
+  return pr;
+}
+
+PairDev offset_pairs(const PairDev& b, int off) {
+  PairDev r;
+  r.st1 = b.st1 + off;
+  r.st2 = b.st2 + off;
+  r.ca = b.ca + off;
+  r.cb = b.cb + off;
+  return r;
+}
+
+constexpr int kSumBlocks = 592;  // 4 x 148 SMs
+
+// ------------------------------------------------------------------------------------------
+// device-resident rhoofr over an explicit pair list (states are columns of c0 with stride ldc)
+// `gate`, if non-null, is called before the kernels of batch b are enqueued (host API: wait for
+// that batch's H2D).
+// ------------------------------------------------------------------------------------------
+struct BatchHooks {
+  virtual void before_batch(int /*b*/, int /*pair0*/, int /*np*/) {}
+  virtual void after_batch(int /*b*/, int /*pair0*/, int /*np*/) {}
+  virtual ~BatchHooks() {}
+};
+
+void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const std::vector<PairHost>& pairs_in,
+                const std::vector<double>& fa_in, const std::vector<double>& fb_in, double* rho,
+                cudaStream_t st, BatchHooks* hooks) {
+  PairDev pr = upload_pairs(p, pairs_in, fa_in, fb_in, st);
+  const int np = (int)pairs_in.size();
+  int b = 0;
+  for (int off = 0; off < np; off += p->max_batch, ++b) {
+    const int nb = std::min(p->max_batch, np - off);
+    if (hooks) hooks->before_batch(b, off, nb);
+    PairDev prb = offset_pairs(pr, off);
+    p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb);
+    p->ky->y_inv(st, p->T1, p->T2, p->pd, nb);
+    p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb);
+    p->launches += 3;
+    if (hooks) hooks->after_batch(b, off, nb);
+  }
+  rt::check_last("rhoofr kernels");
+}
+
+void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector<PairHost>& pairs,
+              const std::vector<double>& fi, const std::vector<double>& fip1, const double* vpot,
+              bool accumulate, cudaStream_t st, BatchHooks* hooks) {
+  PairDev pr = upload_pairs(p, pairs, fi, fip1, st);
+  const int np = (int)pairs.size();
+  int b = 0;
+  for (int off = 0; off < np; off += p->max_batch, ++b) {
+    const int nb = std::min(p->max_batch, np - off);
+    if (hooks) hooks->before_batch(b, off, nb);
+    PairDev prb = offset_pairs(pr, off);
+    p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb);
+    p->ky->y_inv(st, p->T1, p->T2, p->pd, nb);
+    p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb);
+    p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb);
+    p->kx->x_fwd(st, p->T1, c0, c2, ldc, p->pd, prb, nb, accumulate);
+    p->launches += 5;
+    if (hooks) hooks->after_batch(b, off, nb);
+  }
+  rt::check_last("vpsi kernels");
+}
+
+// kin_energy + dotp partial sums for states [first, first+count) of c0 -> d_red[0 .. 2*count)
+void launch_kin(cpb_plan* p, const cplx* c0, long ldc, int first, int count, cudaStream_t st) {
+  if (count <= 0) return;
+  auto k = k_kin_energy;
+  CPB_LAUNCH(k, dim3(count), dim3(256), 2 * 256 * sizeof(double), st, c0, ldc, first, p->ngw, p->geq0,
+             (const double*)p->d_hg, p->d_red);
+  p->launches += 1;
+}
+
+void launch_sum(cpb_plan* p, const double* a, size_t n, double* out, cudaStream_t st) {
+  auto k = k_sum;
+  CPB_LAUNCH(k, dim3(kSumBlocks), dim3(256), 256 * sizeof(double), st, a, n, out);
+  p->launches += 1;
+}
+
+void vpsi_coefs(const std::vector<PairHost>& pairs, const double* f, bool tksham, std::vector<double>& fi,
+                std::vector<double>& fip1) {
+  // vpsi_utils.mod.F90:627-633
+  fi.resize(pairs.size());
+  fip1.resize(pairs.size());
+  for (size_t i = 0; i < pairs.size(); ++i) {
+    double a = f[pairs[i].s1] * 0.5;
+    if (a == 0.0) a = tksham ? 0.5 : 1.0;
+    double b = 0.0;
+    if (pairs[i].s2 >= 0) b = f[pairs[i].s2] * 0.5;
+    if (b == 0.0) b = tksham ? 0.5 : 1.0;
+    fi[i] = a;
+    fip1[i] = b;
+  }
+}
+
+void rho_coefs(cpb_plan* p, const std::vector<PairHost>& all, const double* f, std::vector<PairHost>& pairs,
+               std::vector<double>& ca, std::vector<double>& cb) {
+  // rhoofr_utils.mod.F90:312-316 (skip a pair only if both occupations vanish), :369-374
+  for (const PairHost& q : all) {
+    const double f1 = f[q.s1];
+    const double f2 = q.s2 >= 0 ? f[q.s2] : 0.0;
+    if (f1 == 0.0 && f2 == 0.0) continue;
+    pairs.push_back(q);
+    ca.push_back(f1 / p->omega);
+    cb.push_back(f2 / p->omega);
+  }
+}
+
+// finish rhoofr: scalars from d_red (layout: [2*count kin/dotp][kSumBlocks rho partials])
+void finish_rho_scalars(cpb_plan* p, const double* f, int first, int count, double* ekin, double* rsum_g,
+                        double* rsum_r) {
+  double xkin = 0.0, rsum = 0.0;
+  for (int i = 0; i < count; ++i) {
+    const double fi = f[first + i];
+    if (fi != 0.0) {  // kin_energy_utils.mod.F90:66
+      rsum += fi * p->h_red[2 * i + 1];
+      xkin += fi * p->h_red[2 * i];
+    }
+  }
+  double s = 0.0;
+  for (int i = 0; i < kSumBlocks; ++i) s += p->h_red[2 * count + i];
+  if (ekin) *ekin = xkin * p->tpiba2;
+  if (rsum_g) *rsum_g = rsum;
+  if (rsum_r) *rsum_r = s * p->omega / ((double)p->nr[0] * p->nr[1] * p->nr[2]);
+}
+
+int check_common(cpb_plan* p, const void* c0, long ld, int nstate, const double* f, int ngroups,
+                 int my_group) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  if (!c0 || !f) return fail(CPB_ERR_INVALID, "null c0 or f");
+  if (ld < p->ngw) return fail(CPB_ERR_INVALID, "leading dimension of c0 smaller than ngw");
+  if (nstate < 0) return fail(CPB_ERR_INVALID, "negative nstate");
+  if (ngroups < 1 || my_group < 0 || my_group >= ngroups)
+    return fail(CPB_ERR_INVALID, "bad (ngroups, my_group)");
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* cpb_last_error(void) { return g_last_error.c_str(); }
+
+const char* cpb_version(void) {
+#if defined(CPB_EMULATE)
+  return "cpb200 0.1 (CPU kernel simulator build - tests only)";
+#else
+  return "cpb200 0.1 (sm_100a)";
+#endif
+}
+
+int cpb_length_supported(int n) { return find_axis_kernels(n) ? 1 : 0; }
+
+int cpb_part_1d_nbr_el_in_blk(int n_elem, int proc, int nproc) { return nbr_el_in_blk(n_elem, proc, nproc); }
+int cpb_part_1d_get_el_in_blk(int i_elem, int n_elem, int proc, int nproc) {
+  return get_el_in_blk(i_elem, n_elem, proc, nproc);
+}
+
+int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const int32_t* inyh,
+                    const double* hg, double tpiba2, double omega, int device, int max_batch_pairs) {
+  if (!out || !nr || !kr || !inyh || !hg) return fail(CPB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (ngw <= 0) return fail(CPB_ERR_INVALID, "ngw must be positive");
+  if (omega <= 0.0) return fail(CPB_ERR_INVALID, "omega must be positive");
+  for (int d = 0; d < 3; ++d) {
+    if (nr[d] < 2 || kr[d] < nr[d]) return fail(CPB_ERR_INVALID, "bad mesh / leading dimensions");
+  }
+  cpb_plan* p = nullptr;
+  try {
+    p = new cpb_plan();
+    for (int d = 0; d < 3; ++d) {
+      p->nr[d] = nr[d];
+      p->kr[d] = kr[d];
+    }
+    p->ngw = ngw;
+    p->tpiba2 = tpiba2;
+    p->omega = omega;
+    p->device = device;
+    p->max_batch = max_batch_pairs > 0 ? max_batch_pairs : 16;
+    p->kx = find_axis_kernels(nr[0]);
+    p->ky = find_axis_kernels(nr[1]);
+    p->kz = find_axis_kernels(nr[2]);
+    if (!p->kx || !p->ky || !p->kz) {
+      char buf[160];
+      std::snprintf(buf, sizeof buf, "mesh %dx%dx%d: a length has no kernel instantiation (see sizes.def)",
+                    nr[0], nr[1], nr[2]);
+      throw Error(CPB_ERR_UNSUPPORTED, buf);
+    }
+    const int n1 = nr[0], n2 = nr[1], n3 = nr[2];
+    const int SL = p->kx->sl, LD = SL + 1;
+    if ((long)n1 * LD > 65535) throw Error(CPB_ERR_UNSUPPORTED, "n1 too large for 16-bit tile locations");
+
+    // ---- 0-based box positions; the mirror of g is n-g (inyh -> 2*nh-inyh, fftprp :272-277)
+    std::vector<int> gx(ngw), gy(ngw), gz(ngw);
+    for (int i = 0; i < ngw; ++i) {
+      gx[i] = inyh[3 * (size_t)i + 0] - 1;
+      gy[i] = inyh[3 * (size_t)i + 1] - 1;
+      gz[i] = inyh[3 * (size_t)i + 2] - 1;
+      if (gx[i] < 1 || gx[i] > n1 - 1 || gy[i] < 1 || gy[i] > n2 - 1 || gz[i] < 1 || gz[i] > n3 - 1)
+        throw Error(CPB_ERR_INVALID, "inyh entry (or its -G mirror) falls outside the mesh");
+    }
+    p->geq0 = (gx[0] == n1 / 2 && gy[0] == n2 / 2 && gz[0] == n3 / 2) ? 1 : 0;
+    for (int i = 1; i < ngw; ++i) {
+      if (gx[i] == n1 / 2 && gy[i] == n2 / 2 && gz[i] == n3 / 2)
+        throw Error(CPB_ERR_INVALID, "G=0 must be the first plane wave (loadpa sort order)");
+    }
+
+    // ---- ray marks (fftprp_utils.mod.F90:145-156)
+    std::vector<unsigned char> mark((size_t)n2 * n3, 0);
+    int xlo = n1, xhi = -1;
+    for (int i = 0; i < ngw; ++i) {
+      mark[(size_t)gz[i] * n2 + gy[i]] = 1;
+      mark[(size_t)(n3 - gz[i]) * n2 + (n2 - gy[i])] = 1;
+      xlo = std::min(xlo, std::min(gx[i], n1 - gx[i]));
+      xhi = std::max(xhi, std::max(gx[i], n1 - gx[i]));
+    }
+    int zlo = n3, zhi = -1;
+    for (int z = 0; z < n3; ++z)
+      for (int y = 0; y < n2; ++y)
+        if (mark[(size_t)z * n2 + y]) {
+          zlo = std::min(zlo, z);
+          zhi = std::max(zhi, z);
+        }
+    const int nzb = zhi - zlo + 1;
+    std::vector<int> ylo(nzb), yhi(nzb), rayoff(nzb);
+    // reference ray numbering (z outer, y inner, marked rays only; fftprp :209-217)
+    std::vector<int> refray((size_t)n2 * n3, -1);
+    int nref = 0, nrays = 0;
+    for (int z = zlo; z <= zhi; ++z) {
+      int lo = n2, hi = -1;
+      for (int y = 0; y < n2; ++y)
+        if (mark[(size_t)z * n2 + y]) {
+          refray[(size_t)z * n2 + y] = nref++;
+          lo = std::min(lo, y);
+          hi = std::max(hi, y);
+        }
+      if (hi < 0) {
+        lo = 1;
+        hi = 0;
+      }
+      ylo[z - zlo] = lo;
+      yhi[z - zlo] = hi;
+      rayoff[z - zlo] = nrays;
+      nrays += hi - lo + 1;
+    }
+    auto ray_of = [&](int y, int z) -> int {
+      const int zr = z - zlo;
+      if (zr < 0 || zr >= nzb || y < ylo[zr] || y > yhi[zr]) return -1;
+      return rayoff[zr] + (y - ylo[zr]);
+    };
+    p->nzhs.resize(ngw);
+    p->indzs.resize(ngw);
+    for (int i = 0; i < ngw; ++i) {
+      p->nzhs[i] = gx[i] + 1 + refray[(size_t)gz[i] * n2 + gy[i]] * kr[0];
+      p->indzs[i] = (n1 - gx[i]) + 1 + refray[(size_t)(n3 - gz[i]) * n2 + (n2 - gy[i])] * kr[0];
+    }
+
+    // ---- mirror-closed ray tiles for the x pass
+    std::vector<int> tile_of(nrays, -1), slot_of(nrays, -1), slot_ray;
+    std::vector<int> ray_y(nrays), ray_z(nrays);
+    for (int zr = 0; zr < nzb; ++zr)
+      for (int y = ylo[zr]; y <= yhi[zr]; ++y) {
+        ray_y[rayoff[zr] + y - ylo[zr]] = y;
+        ray_z[rayoff[zr] + y - ylo[zr]] = zr + zlo;
+      }
+    int ntiles = 0;
+    const int half = SL / 2;
+    for (int zr = 0; zr < nzb; ++zr) {
+      int y = ylo[zr];
+      while (y <= yhi[zr]) {
+        if (tile_of[ray_of(y, zr + zlo)] >= 0) {
+          ++y;
+          continue;
+        }
+        const int t = ntiles++;
+        slot_ray.resize((size_t)ntiles * SL, -1);
+        int ns = 0;
+        int na = 0;
+        while (na < half && y <= yhi[zr]) {
+          const int r = ray_of(y, zr + zlo);
+          if (tile_of[r] < 0) {
+            tile_of[r] = t;
+            slot_of[r] = ns;
+            slot_ray[(size_t)t * SL + ns] = r;
+            ++ns;
+            ++na;
+          }
+          ++y;
+        }
+        for (int s = 0; s < na; ++s) {
+          const int r = slot_ray[(size_t)t * SL + s];
+          const int mr = ray_of(n2 - ray_y[r], n3 - ray_z[r]);
+          if (mr < 0) throw Error(CPB_ERR_INVALID, "internal: ray set is not mirror symmetric");
+          if (tile_of[mr] < 0) {
+            tile_of[mr] = t;
+            slot_of[mr] = ns;
+            slot_ray[(size_t)t * SL + ns] = mr;
+            ++ns;
+          } else if (tile_of[mr] != t) {
+            throw Error(CPB_ERR_INVALID, "internal: mirror ray already owned by another tile");
+          }
+        }
+      }
+    }
+
+    // ---- G entries per tile
+    struct Ent {
+      int tile, ig;
+      uint32_t loc;
+    };
+    std::vector<Ent> ents(ngw);
+    {
+      std::vector<unsigned char> occ((size_t)nrays * n1, 0);
+      for (int i = 0; i < ngw; ++i) {
+        const int rp = ray_of(gy[i], gz[i]);
+        const int rm = ray_of(n2 - gy[i], n3 - gz[i]);
+        const int t = tile_of[rp];
+        if (tile_of[rm] != t) throw Error(CPB_ERR_INVALID, "internal: +G and -G rays in different tiles");
+        const uint32_t lp = (uint32_t)(gx[i] * LD + slot_of[rp]);
+        const uint32_t lm = (uint32_t)((n1 - gx[i]) * LD + slot_of[rm]);
+        if (occ[(size_t)rp * n1 + gx[i]]++) throw Error(CPB_ERR_INVALID, "duplicate plane wave in inyh");
+        if (lm != lp) {
+          if (occ[(size_t)rm * n1 + (n1 - gx[i])]++)
+            throw Error(CPB_ERR_INVALID, "inyh contains both G and -G (half-sphere list expected)");
+        } else if (i != 0 || !p->geq0) {
+          throw Error(CPB_ERR_INVALID, "self-mirrored plane wave that is not G=0");
+        }
+        ents[i].tile = t;
+        ents[i].ig = i;
+        ents[i].loc = lp | (lm << 16);
+      }
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.tile < b.tile; });
+    std::vector<int> ent_off(ntiles + 1, 0), ent_ig(ngw);
+    std::vector<uint32_t> ent_loc(ngw);
+    for (int i = 0; i < ngw; ++i) {
+      ent_off[ents[i].tile + 1]++;
+      ent_ig[i] = ents[i].ig;
+      ent_loc[i] = ents[i].loc;
+    }
+    for (int t = 0; t < ntiles; ++t) ent_off[t + 1] += ent_off[t];
+
+    p->xlo = xlo;
+    p->xhi = xhi;
+    p->zlo = zlo;
+    p->nzb = nzb;
+    p->nrays = nrays;
+    p->ref_nrays = nref;
+    p->ntiles = ntiles;
+    p->nent = ngw;
+
+    // ---- device side
+    rt::set_device(device);
+    p->d_ylo = upload(ylo);
+    p->d_yhi = upload(yhi);
+    p->d_rayoff = upload(rayoff);
+    p->d_slot_ray = upload(slot_ray);
+    p->d_ent_off = upload(ent_off);
+    p->d_ent_ig = upload(ent_ig);
+    p->d_ent_loc = upload(ent_loc);
+    p->d_hg = upload(std::vector<double>(hg, hg + ngw));
+    p->d_tw1 = upload(make_twiddles(n1));
+    p->d_tw2 = upload(make_twiddles(n2));
+    p->d_tw3 = upload(make_twiddles(n3));
+    const size_t t1 = (size_t)p->max_batch * nrays * n1 * sizeof(cplx);
+    const size_t t2 = (size_t)p->max_batch * nzb * n2 * n1 * sizeof(cplx);
+    p->T1 = (cplx*)rt::dmalloc(t1);
+    p->T2 = (cplx*)rt::dmalloc(t2);
+    p->workspace_bytes = t1 + t2;
+    p->s_main = rt::stream_create();
+    p->s_in = rt::stream_create();
+    p->s_out = rt::stream_create();
+
+    PlanDev& pd = p->pd;
+    pd.n1 = n1;
+    pd.n2 = n2;
+    pd.n3 = n3;
+    pd.kr1 = kr[0];
+    pd.kr2 = kr[1];
+    pd.kr3 = kr[2];
+    pd.xlo = xlo;
+    pd.xhi = xhi;
+    pd.zlo = zlo;
+    pd.nzb = nzb;
+    pd.nrays = nrays;
+    pd.ntiles = ntiles;
+    pd.ylo = p->d_ylo;
+    pd.yhi = p->d_yhi;
+    pd.rayoff = p->d_rayoff;
+    pd.slot_ray = p->d_slot_ray;
+    pd.ent_off = p->d_ent_off;
+    pd.ent_ig = p->d_ent_ig;
+    pd.ent_loc = p->d_ent_loc;
+    pd.hg = p->d_hg;
+    pd.tw1 = p->d_tw1;
+    pd.tw2 = p->d_tw2;
+    pd.tw3 = p->d_tw3;
+    pd.tpiba2 = tpiba2;
+    pd.inv_n = 1.0 / ((double)n1 * n2 * n3);
+    *out = p;
+    return CPB_OK;
+  } catch (const Error& e) {
+    free_plan(p);
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    free_plan(p);
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+int cpb_plan_destroy(cpb_plan* plan) {
+  if (!plan) return CPB_OK;
+  try {
+    rt::set_device(plan->device);
+  } catch (...) {
+  }
+  free_plan(plan);
+  return CPB_OK;
+}
+
+int cpb_plan_get_info(const cpb_plan* p, cpb_plan_info* info) {
+  if (!p || !info) return fail(CPB_ERR_INVALID, "null argument");
+  for (int d = 0; d < 3; ++d) {
+    info->nr[d] = p->nr[d];
+    info->kr[d] = p->kr[d];
+  }
+  info->ngw = p->ngw;
+  info->geq0 = p->geq0;
+  info->nrays = p->ref_nrays;
+  info->zband = p->nzb;
+  info->xband = p->xhi - p->xlo + 1;
+  info->max_batch = p->max_batch;
+  info->device = p->device;
+  const AxisKernels* ks[3] = {p->kx, p->ky, p->kz};
+  for (int d = 0; d < 3; ++d) {
+    info->radix[d][0] = ks[d]->r1;
+    info->radix[d][1] = ks[d]->r2;
+  }
+  info->workspace_bytes = p->workspace_bytes;
+  return CPB_OK;
+}
+
+int cpb_plan_get_maps(const cpb_plan* p, int32_t* nzhs, int32_t* indzs) {
+  if (!p || !nzhs || !indzs) return fail(CPB_ERR_INVALID, "null argument");
+  std::copy(p->nzhs.begin(), p->nzhs.end(), nzhs);
+  std::copy(p->indzs.begin(), p->indzs.end(), indzs);
+  return CPB_OK;
+}
+
+long cpb_plan_launch_count(const cpb_plan* p) { return p ? p->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ---------------------------------------------------------------------------------------------
+int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, const double* f, int ngroups,
+                   int my_group, double* rhoe_dev, double* ekin, double* rsum_g, double* rsum_r,
+                   unsigned flags, void* stream) {
+  if (int e = check_common(p, c0_dev, ld_c0, nstate, f, ngroups, my_group)) return e;
+  if (!rhoe_dev) return fail(CPB_ERR_INVALID, "null rhoe");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cplx* c0 = (const cplx*)c0_dev;
+    const int nblk = nbr_el_in_blk(nstate, my_group, ngroups);
+    const int first = nblk > 0 ? get_el_in_blk(1, nstate, my_group, ngroups) - 1 : 0;
+    std::vector<PairHost> pairs;
+    std::vector<double> ca, cb;
+    rho_coefs(p, block_pairs(nstate, my_group, ngroups), f, pairs, ca, cb);
+    ensure_red(p, 2 * nblk + kSumBlocks);
+    rt::dzero(rhoe_dev, p->nnr1() * sizeof(double), st);  // rhoofr_utils.mod.F90:198
+    launch_kin(p, c0, ld_c0, first, nblk, st);               // :178
+    run_rhoofr(p, c0, ld_c0, pairs, ca, cb, rhoe_dev, st, nullptr);
+    launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + 2 * nblk, st);  // :607-619
+    rt::d2h(p->h_red, p->d_red, (size_t)(2 * nblk + kSumBlocks) * sizeof(double), st);
+    rt::sync(st);
+    double rg = 0, rr = 0;
+    finish_rho_scalars(p, f, first, nblk, ekin, &rg, &rr);
+    if (rsum_g) *rsum_g = rg;
+    if (rsum_r) *rsum_r = rr;
+    if ((flags & CPB_RHO_CHECK_CHARGE) && ngroups == 1 && std::fabs(rr - rg) > 1.0e-6)
+      return fail(CPB_ERR_CHARGE, "TOTAL DENSITY SUMS ARE NOT EQUAL");  // :625-635
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                 const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
+  if (int e = check_common(p, c0_dev, ld, nstate, f, ngroups, my_group)) return e;
+  if (!c2_dev || !vpot_dev) return fail(CPB_ERR_INVALID, "null c2 or vpot");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups);
+    std::vector<double> fi, fip1;
+    vpsi_coefs(pairs, f, (flags & CPB_VPSI_TKSHAM) != 0, fi, fip1);
+    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, pairs, fi, fip1, vpot_dev,
+             !(flags & CPB_VPSI_OVERWRITE), st, nullptr);
+    rt::sync(st);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+}  // extern "C"
+
+#include "host_api.inc"

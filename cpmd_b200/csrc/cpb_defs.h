@@ -1,0 +1,69 @@
+// Common definitions for the cpb200 library (B200 / sm_100a vpsi + rhoofr path).
+//
+// The same kernel sources compile in two ways:
+//   * nvcc, sm_100a  -> the product (libcpb200.so).
+//   * g++ -DCPB_EMULATE -> tests/emu/libcpb200_emu.so, a *functional simulator* of the CUDA
+//     kernels (one fiber per CUDA thread, __syncthreads = fiber barrier).  It exists because the
+//     authoring container has no GPU: it lets the index arithmetic of every kernel be checked
+//     against the oracle on the CPU.  It is test infrastructure only; the Python package never
+//     loads it (cpmd_b200/lib.py loads libcpb200.so or raises).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <type_traits>
+
+#if defined(CPB_EMULATE)
+#include "emu_cuda.h"
+#define CPB_HD inline
+#define CPB_D inline
+#define CPB_GLOBAL static void
+#define CPB_LAUNCH_BOUNDS(...)
+#define CPB_RESTRICT
+#define CPB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::dyn_smem())
+#define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
+  ::emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define CPB_HD __host__ __device__ __forceinline__
+#define CPB_D __device__ __forceinline__
+#define CPB_GLOBAL __global__ void
+#define CPB_LAUNCH_BOUNDS(...) __launch_bounds__(__VA_ARGS__)
+#define CPB_RESTRICT __restrict__
+#define CPB_DYN_SMEM(type, name)                                   \
+  extern __shared__ __align__(16) unsigned char cpb_dyn_smem_[];   \
+  type* name = reinterpret_cast<type*>(cpb_dyn_smem_)
+#define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
+  kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace cpb {
+
+typedef double2 cplx;
+
+template <int I>
+using IC = std::integral_constant<int, I>;
+
+// Compile-time loop: f(IC<B>{}), f(IC<B+1>{}), ... f(IC<E-1>{}).  Every index is a constant
+// expression inside f, so arrays indexed with it live in registers.
+template <int B, int E, class F>
+CPB_HD void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(IC<B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+CPB_HD cplx mk(double x, double y) {
+  cplx r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+CPB_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+CPB_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+CPB_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+CPB_HD cplx cmulc(cplx a, cplx b) { return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+CPB_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+
+}  // namespace cpb

@@ -1,0 +1,98 @@
+"""ctypes binding of the C ABI in ``include/cpb200.h`` (libcpb200.so, sm_100a).
+
+The product path has no CPU fallback: :func:`load` loads ``cpmd_b200/libcpb200.so`` (built
+in-tree by ``__graft_entry__.build()`` / ``make -C cpmd_b200/csrc``) or raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpb200.so")
+
+# status codes / flags (include/cpb200.h)
+CPB_OK = 0
+CPB_ERR_INVALID = -1
+CPB_ERR_CUDA = -2
+CPB_ERR_NOMEM = -3
+CPB_ERR_UNSUPPORTED = -4
+CPB_ERR_CHARGE = -5
+CPB_VPSI_OVERWRITE = 1
+CPB_VPSI_TKSHAM = 2
+CPB_RHO_CHECK_CHARGE = 1
+CPB_C0_KEEP = 0x10
+CPB_C0_REUSE = 0x20
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("nr", C.c_int * 3),
+        ("kr", C.c_int * 3),
+        ("ngw", C.c_int),
+        ("geq0", C.c_int),
+        ("nrays", C.c_int),
+        ("zband", C.c_int),
+        ("xband", C.c_int),
+        ("max_batch", C.c_int),
+        ("device", C.c_int),
+        ("radix", (C.c_int * 2) * 3),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
+#: every symbol include/cpb200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cpb_last_error": (C.c_char_p, []),
+    "cpb_version": (C.c_char_p, []),
+    "cpb_length_supported": (C.c_int, [C.c_int]),
+    "cpb_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "cpb_plan_destroy": (C.c_int, [C.c_void_p]),
+    "cpb_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
+    "cpb_plan_get_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cpb_part_1d_nbr_el_in_blk": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "cpb_part_1d_get_el_in_blk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cpb_rhoofr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                             C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                             C.POINTER(C.c_double), C.c_uint]),
+    "cpb_vpsi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                           C.c_int, C.c_int, C.c_uint]),
+    "cpb_c0_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int]),
+    "cpb_c0_invalidate": (C.c_int, [C.c_void_p]),
+    "cpb_rhoofr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
+    "cpb_vpsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
+}
+
+
+def declare(cdll: C.CDLL) -> C.CDLL:
+    """Attach restype/argtypes for every exported entry point; raises AttributeError if one is
+    missing from the shared object."""
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(cdll, name)
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+_lib = None
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library.  No fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryNotBuilt(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C cpmd_b200/csrc`. cpmd_b200 has no CPU fallback.")
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib

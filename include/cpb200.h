@@ -1,0 +1,142 @@
+/* cpb200 — B200-native (sm_100a) drop-in for CPMD's Gamma-point `vpsi` + `rhoofr` hot path.
+ *
+ * C ABI: plain pointers and sizes, no C++/torch types.  All entry points return 0 on success or
+ * a negative cpb_status; cpb_last_error() gives the message of the calling thread's last failure
+ * (the Fortran shim turns a non-zero return into CALL stopgm(...), the reference's only error
+ * convention, error_handling.mod.F90:11-53).
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/src):
+ *
+ *   cpb_plan_create   the module-global FFT/G-vector state built by fft_init/fftprp_default_init
+ *                     (fftprp_utils.mod.F90:66-93,139-285: mg ray table, kr3min/kr3max, nzhs,
+ *                     indzs, msp) and setfftn(0) (fftnew_utils.mod.F90:53-175), gathered once into
+ *                     a plan.  Inputs are exactly the globals the Fortran shim can read:
+ *                     spar%nr1s.., fpar%kr1.., ncpw%ngw, inyh(3,ngw), hg(ngw) (cppt.mod.F90:22-45),
+ *                     parm%tpiba2, parm%omega (system.mod.F90:138-151).
+ *   cpb_rhoofr[_dev]  SUBROUTINE rhoofr(c0,rhoe,psi,nstate)        rhoofr_utils.mod.F90:122-644
+ *                     incl. kin_energy (kin_energy_utils.mod.F90:62-110) and the charge sums
+ *                     (rhoofr_utils.mod.F90:607-619).  `psi` (scratch) has no counterpart: the
+ *                     library owns its work space.
+ *   cpb_vpsi[_dev]    SUBROUTINE vpsi(c0,c2,f,vpot,psi,nstate,ikind,ispin,redist_c2)
+ *                                                                  vpsi_utils.mod.F90:120-732
+ *   cpb_part_1d_*     part_1d_nbr_el_in_blk / part_1d_get_el_in_blk   part_1d.mod.F90:22-57
+ *
+ * State groups (CP_GROUPS, set_cp_grp_utils.mod.F90:77-83): every call takes (ngroups, my_group)
+ * and processes only the group's contiguous block of states, pairing states inside the block
+ * exactly like the reference loops (vpsi_utils.mod.F90:376-383, rhoofr_utils.mod.F90:306-310).
+ * The cross-group reductions stay with the caller, where the reference has them:
+ * cp_grp_redist(rhoe) (rhoofr_utils.mod.F90:457-461) and, if wanted, cp_grp_redist(c2)
+ * (vpsi_utils.mod.F90:708-712 / forces_driver.mod.F90:283).  Deviation, documented in
+ * ekin / rsum_g are returned for the group's block only (the reference computes
+ * them redundantly over all states on every group) — sum them over groups together with rhoe.
+ *
+ * Layout conventions are the reference's: c0/c2 are column-major (ld, nstate) COMPLEX*16, one
+ * column per state, ngw <= ld; rhoe/vpot are REAL*8 (kr1, kr2s, kr3s) x-fastest with the
+ * odd-padded leading dimensions of leadim (loadpa_utils.mod.F90:509-525); inyh is INTEGER*4
+ * (3,ngw), 1-based.  Only the supported variant is implemented: Gamma point, no LSD/LSE, no
+ * tau, no double grid, akin = 0 — the shim must route everything else to the original routine
+ * (list in INTEGRATION.md).
+ */
+#ifndef CPB200_H
+#define CPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cpb_plan cpb_plan;
+
+typedef enum {
+  CPB_OK = 0,
+  CPB_ERR_INVALID = -1,     /* bad argument / unsupported mesh length / inconsistent G list */
+  CPB_ERR_CUDA = -2,        /* CUDA runtime failure */
+  CPB_ERR_NOMEM = -3,
+  CPB_ERR_UNSUPPORTED = -4, /* requested variant is outside the implemented path */
+  CPB_ERR_CHARGE = -5       /* |rsum_r - rsum_g| > 1e-6 (rhoofr_utils.mod.F90:625-635), opt-in */
+} cpb_status;
+
+/* flags for cpb_vpsi / cpb_rhoofr */
+#define CPB_VPSI_OVERWRITE 1u /* c2 = result instead of the reference's c2 += result */
+#define CPB_VPSI_TKSHAM 2u    /* cntl%tksham: f==0 -> fi=0.5 instead of 1 (vpsi_utils:628-633) */
+#define CPB_RHO_CHECK_CHARGE 1u /* return CPB_ERR_CHARGE like the reference's stopgm */
+/* host-pointer entry points only: device-side cache of the group's c0 block */
+#define CPB_C0_KEEP 0x10u  /* after this call the uploaded block stays valid on the device */
+#define CPB_C0_REUSE 0x20u /* skip the upload if (c0 pointer, ld, nstate, group) match the kept block */
+
+typedef struct {
+  int nr[3];          /* mesh */
+  int kr[3];          /* padded leading dimensions */
+  int ngw;
+  int geq0;           /* first plane wave is G=0 (derived from inyh) */
+  int nrays;          /* rays transformed by the x pass (== msrays for a convex cutoff) */
+  int zband;          /* kr3max-kr3min+1 */
+  int xband;          /* x extent holding coefficients */
+  int max_batch;      /* packed pairs per kernel batch */
+  int device;
+  int radix[3][2];    /* two-pass factorisation of each axis */
+  size_t workspace_bytes;
+} cpb_plan_info;
+
+const char* cpb_last_error(void);
+const char* cpb_version(void);
+
+/* 1 if mesh length n has a kernel instantiation in this build, else 0 */
+int cpb_length_supported(int n);
+
+/* nr, kr: 3 ints each.  inyh: (3,ngw) column-major INTEGER*4, 1-based (cppt inyh).  hg: |G|^2 in
+ * units of tpiba2.  device: CUDA ordinal.  max_batch_pairs: pairs per batch (<=0: default 16). */
+int cpb_plan_create(cpb_plan** plan, const int* nr, const int* kr, int ngw, const int32_t* inyh,
+                    const double* hg, double tpiba2, double omega, int device,
+                    int max_batch_pairs);
+int cpb_plan_destroy(cpb_plan* plan);
+int cpb_plan_get_info(const cpb_plan* plan, cpb_plan_info* info);
+
+/* Reference-compatible index maps derived by the plan (for cross-checking against the host
+ * program's own nzhs/indzs, fftprp_utils.mod.F90:269-285).  Both arrays have ngw entries, 1-based
+ * into (kr1s, nrays) ray storage with the reference's ray numbering. */
+int cpb_plan_get_maps(const cpb_plan* plan, int32_t* nzhs, int32_t* indzs);
+
+/* part_1d.mod.F90:22-57 (proc is 0-based, elements 1-based, as in the reference) */
+int cpb_part_1d_nbr_el_in_blk(int n_elem, int proc, int nproc);
+int cpb_part_1d_get_el_in_blk(int i_elem, int n_elem, int proc, int nproc);
+
+/* ---- host-pointer entry points: what the Fortran shim binds --------------------------------
+ * Arrays live in host memory; the library stages them (pinned bounce buffers, copies overlapped
+ * with the kernels of the previous batch) and copies the results back before returning. */
+int cpb_rhoofr(cpb_plan* plan, const void* c0, long ld_c0, int nstate, const double* f,
+               int ngroups, int my_group, double* rhoe, double* ekin, double* rsum_g,
+               double* rsum_r, unsigned flags);
+
+int cpb_vpsi(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, const double* f,
+             const double* vpot, int ngroups, int my_group, unsigned flags);
+
+/* Optional: keep the group's block of c0 on the device between rhoofr and the following vpsi of
+ * the same MD step (the reference's cp_cuwfn cache, vpsi_utils.mod.F90:268-273, which trusts a
+ * checksum of the first state; here the caller states it explicitly).  After cpb_c0_upload, or a
+ * host call made with CPB_C0_KEEP, host entry points called with CPB_C0_REUSE and the same c0
+ * pointer, ld, nstate and group reuse the device copy; cpb_c0_invalidate drops it. */
+int cpb_c0_upload(cpb_plan* plan, const void* c0, long ld_c0, int nstate, int ngroups, int my_group);
+int cpb_c0_invalidate(cpb_plan* plan);
+
+/* ---- device-pointer entry points (benchmark / Python harness, multi-GPU driver) ------------
+ * c0/c2/rhoe/vpot are device pointers on the plan's device; f is a host array; stream is a
+ * cudaStream_t (NULL = default stream).  The call returns after the stream work completed
+ * (scalars are written to host memory). */
+int cpb_rhoofr_dev(cpb_plan* plan, const void* c0_dev, long ld_c0, int nstate, const double* f,
+                   int ngroups, int my_group, double* rhoe_dev, double* ekin, double* rsum_g,
+                   double* rsum_r, unsigned flags, void* stream);
+
+int cpb_vpsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate,
+                 const double* f, const double* vpot_dev, int ngroups, int my_group,
+                 unsigned flags, void* stream);
+
+/* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
+long cpb_plan_launch_count(const cpb_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPB200_H */

@@ -1,0 +1,395 @@
+"""CPU oracle for CPMD's Gamma-point ``vpsi`` + ``rhoofr`` hot path (NumPy/SciPy, FP64).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product: it may be imported
+only by ``tests/``, by ``__graft_entry__.smoke()`` and by the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py``, and always as the *checker*, never as the thing that is shipped
+or measured as the GPU path.
+
+PARITY UNPINNED: the reference tree (/root/reference, CPMD 4.3) ships no golden vectors,
+known-answer tests or fixtures for this path, and it cannot be compiled in the authoring container
+(Fortran 2008 + FFTW + MPI; no Fortran compiler is installed).  This file is therefore a
+restatement of the reference arithmetic, function by function, each citing the reference
+file:line it follows (paths relative to /root/reference/src).  It is pinned instead by the
+known-answer tests derived from the reference's own formulas (tests/test_oracle.py) and by an
+independent second restatement (oracle/staged_oracle.c, which follows ``fftnew``'s staged sparse
+pipeline instead of a dense 3-D FFT).
+
+All "Fortran" indices kept in arrays here are 1-based exactly like the reference's (``inyh``,
+``nzhs``, ``indzs``); they are converted at the point of use.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.fft as sfft
+
+# ----------------------------------------------------------------------------------------------
+# mesh helpers
+# ----------------------------------------------------------------------------------------------
+
+#: admissible FFT lengths, roots 2,3,5,7 (fftchk_utils.mod.F90:75-97, first part of the LFT table)
+LFT = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 27, 28, 30, 32, 35, 36, 40,
+       42, 45, 48, 49, 50, 54, 56, 60, 63, 64, 70, 72, 75, 80, 81, 84, 90, 96, 98, 100, 105, 108,
+       112, 120, 125, 126, 128, 135, 140, 144, 147, 150, 160, 162, 168, 175, 180, 189, 192, 196,
+       200, 210, 216, 224, 225, 240, 243, 245, 250, 252, 256, 270, 280, 288, 294, 300, 315, 320,
+       324, 336, 343, 350, 360, 375, 378, 384, 392, 400, 405, 420, 432, 441, 448, 450, 480, 486,
+       490, 500, 504, 512]
+
+
+def fftchk(m: int, n: int = 2) -> int:
+    """Next admissible FFT length >= m (n=1) / next even one (n=2); fftchk_utils.mod.F90:60-131."""
+    for v in LFT:
+        if v >= m and (n == 1 or v % 2 == 0):
+            return v
+    raise ValueError("mesh too large for table")
+
+
+def leadim(nr: int) -> int:
+    """Odd-padded leading dimension kr = nr + MOD(nr+1,2); loadpa_utils.mod.F90:509-525."""
+    return nr + (nr + 1) % 2
+
+
+# ----------------------------------------------------------------------------------------------
+# G vectors (loadpa) and FFT index maps (fftprp)
+# ----------------------------------------------------------------------------------------------
+
+@dataclass
+class Geometry:
+    nr: tuple          # (nr1s, nr2s, nr3s)
+    kr: tuple          # (kr1s, kr2s, kr3s) padded leading dimensions
+    ngw: int
+    inyh: np.ndarray   # (3, ngw) int32, 1-based box position of +G  (loadpa_utils.mod.F90:306-308)
+    hg: np.ndarray     # (ngw,) |G|^2 in units of tpiba2              (rggen_utils.mod.F90:121-129)
+    geq0: bool         # first vector is G=0                          (loadpa_utils.mod.F90:414-420)
+    nrays: int         # ngrays = msrays
+    mg: np.ndarray     # (kr2s, kr3s) int32 ray number (1-based) or 0 (fftprp_utils.mod.F90:209-217)
+    nzhs: np.ndarray   # (ngw,) int32 1-based index of +G into ray storage (kr1s, nrays)
+    indzs: np.ndarray  # (ngw,) int32 1-based index of -G
+    kr3min: int        # 1-based z band (fftprp_utils.mod.F90:177-192)
+    kr3max: int
+    msp2: np.ndarray   # (nrays,) ray -> y + (z-kr3min)*kr2s, 1-based   (fftprp_utils.mod.F90:259-268)
+
+    @property
+    def nnr1(self):
+        return self.kr[0] * self.kr[1] * self.kr[2]
+
+
+def gvectors(nr, gcutw, b=None):
+    """Half-sphere G enumeration of ``loadpa`` (loadpa_utils.mod.F90:282-335) restricted to the
+    wavefunction cutoff |G|^2 < gcutw, followed by the |G|^2 sort (:408, gsort :748-792).
+
+    Enumeration rule: i>=0; i==0 => j>=0; i==j==0 => k>=0.  ``inyh = nh + (i,j,k)``,
+    ``nh = nr/2+1``.  The order inside a |G|^2 shell is an implementation detail of the
+    reference's sort (symmetry broken by a sqrt(ig-1)*eps perturbation); neither vpsi nor rhoofr
+    depend on it, so a stable sort on the exact |G|^2 (enumeration order inside a shell) is used,
+    which puts G=0 first exactly like the reference.
+    Returns (inyh(3,ngw) int32 1-based, hg(ngw) float64).
+    """
+    nr1, nr2, nr3 = nr
+    if b is None:
+        b = np.eye(3)
+    b = np.asarray(b, dtype=np.float64)
+    nh = (nr1 // 2 + 1, nr2 // 2 + 1, nr3 // 2 + 1)
+    i = np.arange(0, nr1)
+    j = np.arange(-nr2 + 1, nr2)
+    k = np.arange(-nr3 + 1, nr3)
+    # limit the candidate ranges by a bounding box (pure speed-up, same set)
+    bn = np.linalg.norm(np.linalg.inv(b), axis=0)  # |G_i| >= |i| / |a_i|-ish bound; conservative
+    rad = np.sqrt(gcutw)
+    i = i[i <= rad * bn[0] + 1]
+    j = j[np.abs(j) <= rad * bn[1] + 1]
+    k = k[np.abs(k) <= rad * bn[2] + 1]
+    I, J, K = np.meshgrid(i, j, k, indexing="ij")  # enumeration order: i outer, j, k inner
+    I = I.ravel(); J = J.ravel(); K = K.ravel()
+    keep = (I > 0) | ((I == 0) & (J > 0)) | ((I == 0) & (J == 0) & (K >= 0))
+    I, J, K = I[keep], J[keep], K[keep]
+    t = I[:, None] * b[0][None, :] + J[:, None] * b[1][None, :] + K[:, None] * b[2][None, :]
+    g2 = (t * t).sum(axis=1)
+    sel = g2 < gcutw
+    I, J, K, g2 = I[sel], J[sel], K[sel], g2[sel]
+    order = np.argsort(g2, kind="stable")
+    I, J, K, g2 = I[order], J[order], K[order], g2[order]
+    inyh = np.stack([nh[0] + I, nh[1] + J, nh[2] + K]).astype(np.int32)
+    # box must contain both +G and -G without touching index 1 whose mirror falls outside
+    for d in range(3):
+        if inyh[d].min() < 2 or inyh[d].max() > nr[d]:
+            raise ValueError("cutoff sphere does not fit the mesh (dual < 4?)")
+    return inyh, g2.astype(np.float64)
+
+
+def fft_maps(nr, inyh, hg) -> Geometry:
+    """``fftprp_default_init`` for one rank per group (fftprp_utils.mod.F90:139-285)."""
+    nr1, nr2, nr3 = nr
+    kr = (leadim(nr1), leadim(nr2), leadim(nr3))
+    nh1, nh2, nh3 = nr1 // 2 + 1, nr2 // 2 + 1, nr3 // 2 + 1
+    ngw = inyh.shape[1]
+    ny1, ny2, ny3 = (inyh[0].astype(np.int64), inyh[1].astype(np.int64), inyh[2].astype(np.int64))
+    iny1, iny2, iny3 = 2 * nh1 - ny1, 2 * nh2 - ny2, 2 * nh3 - ny3          # :147-148, :272-277
+    mg = np.zeros((kr[1] + 1, kr[2] + 1), dtype=np.int64)                   # 1-based, [0] unused
+    mg[ny2, ny3] = 1
+    mg[iny2, iny3] = 1                                                      # :149-150
+    mz = np.zeros(kr[2] + 2, dtype=np.int64)
+    mz[ny3] = 1
+    mz[iny3] = 1
+    zs = np.nonzero(mz)[0]
+    kr3min, kr3max = int(zs.min()), int(zs.max())                           # :177-192
+    # ray numbering: z outer, y inner (:209-217)
+    img = 0
+    for jz in range(1, kr[2] + 1):
+        ys = np.nonzero(mg[1:, jz])[0] + 1
+        for iy in ys:
+            img += 1
+            mg[iy, jz] = img
+    nrays = img
+    nzhs = ny1 + (mg[ny2, ny3] - 1) * kr[0]                                 # :278
+    indzs = iny1 + (mg[iny2, iny3] - 1) * kr[0]                             # :279
+    msp2 = np.zeros(nrays, dtype=np.int64)
+    yy, zz = np.nonzero(mg)
+    msp2[mg[yy, zz] - 1] = yy + (zz - kr3min) * kr[1]                       # :259-268
+    geq0 = bool(hg[0] < 1.0e-5)                                             # loadpa :414-420
+    return Geometry(nr=tuple(nr), kr=kr, ngw=ngw, inyh=inyh, hg=hg, geq0=geq0, nrays=nrays,
+                    mg=mg[1:, 1:].astype(np.int32), nzhs=nzhs.astype(np.int32),
+                    indzs=indzs.astype(np.int32), kr3min=kr3min, kr3max=kr3max,
+                    msp2=msp2.astype(np.int32))
+
+
+def make_geometry(nr, gcutw=None, b=None) -> Geometry:
+    """Convenience: synthetic cubic-cell geometry with dual 4: gcutw = (n/4)^2."""
+    if isinstance(nr, int):
+        nr = (nr, nr, nr)
+    if gcutw is None:
+        gcutw = (min(nr) / 4.0) ** 2
+    inyh, hg = gvectors(nr, gcutw, b)
+    return fft_maps(nr, inyh, hg)
+
+
+# ----------------------------------------------------------------------------------------------
+# state-group decomposition (part_1d)
+# ----------------------------------------------------------------------------------------------
+
+def part_1d_nbr_el_in_blk(n_elem, proc, nproc):
+    """part_1d.mod.F90:22-38."""
+    res = n_elem % nproc
+    nbr = (n_elem - res) // nproc
+    return nbr + 1 if proc < res else nbr
+
+
+def part_1d_get_el_in_blk(i_elem, n_elem, proc, nproc):
+    """1-based element -> 1-based global index; part_1d.mod.F90:41-57."""
+    res = n_elem % nproc
+    nbr = (n_elem - res) // nproc
+    return i_elem + nbr * proc + min(proc, res)
+
+
+def state_pairs(nstate, group=0, ngroups=1):
+    """Pairs (is1, is2) (0-based; is2 = None for a trailing single state) formed inside the
+    group's block exactly like the hot loops (vpsi_utils.mod.F90:377-383,
+    rhoofr_utils.mod.F90:306-310)."""
+    nblk = part_1d_nbr_el_in_blk(nstate, group, ngroups)
+    out = []
+    for i in range(1, nblk + 1, 2):
+        is1 = part_1d_get_el_in_blk(i, nstate, group, ngroups)
+        is2 = part_1d_get_el_in_blk(i + 1, nstate, group, ngroups) if i + 1 <= nblk else None
+        out.append((is1 - 1, None if is2 is None else is2 - 1))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# packing, transforms
+# ----------------------------------------------------------------------------------------------
+
+def set_psi_2_states_g(geo: Geometry, c1, c2):
+    """psi(nzfs)=c1+i*c2, psi(inzs)=conj(c1)+i*conj(c2), G=0 rewritten last
+    (state_utils.mod.F90:171-189).  Returns ray storage psi(kr1s*nrays)."""
+    psi = np.zeros(geo.kr[0] * geo.nrays, dtype=np.complex128)
+    psi[geo.nzhs - 1] = c1 + 1j * c2
+    psi[geo.indzs - 1] = np.conj(c1) + 1j * np.conj(c2)
+    if geo.geq0:
+        psi[geo.nzhs[0] - 1] = c1[0] + 1j * c2[0]
+    return psi
+
+
+def set_psi_1_state_g(geo: Geometry, c1, alpha=1.0):
+    """state_utils.mod.F90:132-168."""
+    psi = np.zeros(geo.kr[0] * geo.nrays, dtype=np.complex128)
+    psi[geo.nzhs - 1] = alpha * c1
+    psi[geo.indzs - 1] = alpha * np.conj(c1)
+    if geo.geq0:
+        psi[geo.nzhs[0] - 1] = alpha * c1[0]
+    return psi
+
+
+def _rays_to_box(geo: Geometry, psi_rays):
+    """Ray storage (kr1s, nrays) -> dense box [z, y, x] of the true mesh size (zeros elsewhere).
+    Ray r sits at (y,z) with mg(y,z)=r (fftprp_utils.mod.F90:209-217)."""
+    n1, n2, n3 = geo.nr
+    rays = psi_rays.reshape(geo.nrays, geo.kr[0])
+    box = np.zeros((n3, n2, n1), dtype=np.complex128)
+    yy, zz = np.nonzero(geo.mg[:n2, :n3])
+    r = geo.mg[yy, zz] - 1
+    box[zz, yy, :] = rays[r, :n1]
+    return box
+
+
+def _box_to_rays(geo: Geometry, box):
+    n1, n2, n3 = geo.nr
+    rays = np.zeros((geo.nrays, geo.kr[0]), dtype=np.complex128)
+    yy, zz = np.nonzero(geo.mg[:n2, :n3])
+    r = geo.mg[yy, zz] - 1
+    rays[r, :n1] = box[zz, yy, :]
+    return rays.reshape(-1)
+
+
+def invfftn_sparse(geo: Geometry, psi_rays):
+    """``invfftn(psi,.TRUE.)`` = fftnew(isign=-1, sparse) (fftmain_utils.mod.F90:373-401, 92-104):
+    unnormalised e^{+i...} transform, box index as frequency (no phase factor in the sparse
+    branch), result in the padded real-space layout (kr1, kr2s, kr3s), x fastest, pads zero
+    (mltfft_utils.mod.F90:227-253).  The dense 3-D transform of the zero-filled box is the same
+    linear map as the staged x/y/z passes."""
+    n1, n2, n3 = geo.nr
+    box = _rays_to_box(geo, psi_rays)
+    r = sfft.ifftn(box, norm="forward", workers=-1)      # "forward" => no 1/N on the inverse
+    out = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]), dtype=np.complex128)
+    out[:n3, :n2, :n1] = r
+    return out.reshape(-1)
+
+
+def fwfftn_sparse(geo: Geometry, psi_r):
+    """``fwfftn(psi,.TRUE.)`` = fftnew(isign=+1, sparse): e^{-i...} with scale 1/(n1 n2 n3)
+    applied in the last pass (fftmain_utils.mod.F90:403-431, 122-136); returns ray storage."""
+    n1, n2, n3 = geo.nr
+    box = psi_r.reshape(geo.kr[2], geo.kr[1], geo.kr[0])[:n3, :n2, :n1]
+    g = sfft.fftn(box, norm="forward", workers=-1)       # "forward" => 1/N on the forward
+    return _box_to_rays(geo, g)
+
+
+# ----------------------------------------------------------------------------------------------
+# G-space reductions
+# ----------------------------------------------------------------------------------------------
+
+def dotp(geo: Geometry, a, b):
+    """dotp_utils.mod.F90:26-53 — half-sphere weight 2, G=0 weight 1."""
+    if geo.geq0:
+        d = a[0].real * b[0].real
+    else:
+        d = 2.0 * (a[0].real * b[0].real + a[0].imag * b[0].imag)
+    if a.shape[0] > 1:
+        d += 2.0 * float(np.dot(a[1:].real, b[1:].real) + np.dot(a[1:].imag, b[1:].imag))
+    return float(d)
+
+
+def kin_energy(geo: Geometry, c0, f, tpiba2):
+    """kin_energy_utils.mod.F90:62-110 (akin == 0 branch).  c0 is (nstate, ngw) here (each row one
+    Fortran column c0(:,i)).  Returns (ekin, rsum)."""
+    rsum = 0.0
+    xkin = 0.0
+    for i in range(c0.shape[0]):
+        if f[i] != 0.0:
+            rsum += f[i] * dotp(geo, c0[i], c0[i])
+            sk1 = float(np.sum(geo.hg * (c0[i].real ** 2 + c0[i].imag ** 2)))
+            xkin += f[i] * sk1
+    return xkin * tpiba2, rsum
+
+
+# ----------------------------------------------------------------------------------------------
+# the two hot routines
+# ----------------------------------------------------------------------------------------------
+
+def rhoofr(geo: Geometry, c0, f, omega, tpiba2, group=0, ngroups=1):
+    """``rhoofr`` (rhoofr_utils.mod.F90:122-644), Gamma point, no LSD/LSE/tau/double grid.
+
+    c0: (nstate, ngw) complex128.  Returns dict(rhoe (nnr1,), ekin, rsum_g, rsum_r) where rhoe is
+    the *group-partial* density when ngroups>1 (the caller sums over groups, cp_grp_redist
+    :457-461) and ekin/rsum_g are computed over all states as the reference does (:178)."""
+    nstate = c0.shape[0]
+    ekin, rsum = kin_energy(geo, c0, f, tpiba2)                       # :178
+    rhoe = np.zeros(geo.nnr1, dtype=np.float64)                       # :198
+    for is1, is2 in state_pairs(nstate, group, ngroups):              # :306-310
+        tfcal = f[is1] != 0.0 or (is2 is not None and f[is2] != 0.0)  # :312-316
+        if not tfcal:
+            continue
+        if is2 is None:
+            psi = set_psi_1_state_g(geo, c0[is1])                     # :329-330
+        else:
+            psi = set_psi_2_states_g(geo, c0[is1], c0[is2])           # :332
+        psi = invfftn_sparse(geo, psi)                                # :346
+        coef3 = f[is1] / omega                                        # :369
+        coef4 = 0.0 if is2 is None else f[is2] / omega                # :370-374
+        rhoe += coef3 * psi.real ** 2 + coef4 * psi.imag ** 2         # density_utils :61-83
+    n1, n2, n3 = geo.nr
+    rsum1 = float(np.sum(rhoe)) * omega / float(n1 * n2 * n3)         # :607-619
+    return dict(rhoe=rhoe, ekin=ekin, rsum_g=rsum, rsum_r=rsum1)
+
+
+def vpsi(geo: Geometry, c0, c2, f, vpot, tpiba2, group=0, ngroups=1, redist_c2=False,
+         tksham=False):
+    """``vpsi`` (vpsi_utils.mod.F90:120-732), Gamma point, RKS, akin == 0.
+
+    c0, c2: (nstate, ngw) complex128 (c2 is accumulated into: ``c2 += C2_vpsi`` :717);
+    vpot: (nnr1,) padded real-space potential.  Only the group's block of states is touched.
+    Returns the new c2 (a copy)."""
+    nstate = c0.shape[0]
+    c2v = np.zeros_like(c2)                                           # :199-203
+    for is1, is2 in state_pairs(nstate, group, ngroups):              # :376-383
+        if is2 is None:
+            psi = set_psi_1_state_g(geo, c0[is1])                     # :432-433
+        else:
+            psi = set_psi_2_states_g(geo, c0[is1], c0[is2])           # :435
+        psi = invfftn_sparse(geo, psi)                                # :443
+        psi = vpot * psi                                              # :487-493
+        psi = fwfftn_sparse(geo, psi)                                 # :552
+        fi = f[is1] * 0.5                                             # :627
+        if fi == 0.0:
+            fi = 0.5 if tksham else 1.0                               # :628-629
+        fip1 = 0.0
+        if is2 is not None:
+            fip1 = f[is2] * 0.5                                       # :631
+        if fip1 == 0.0:
+            fip1 = 0.5 if tksham else 1.0                             # :632-633
+        psin = psi[geo.nzhs - 1]                                      # :662
+        psii = psi[geo.indzs - 1]                                     # :663
+        fp = psin + psii
+        fm = psin - psii
+        g2 = tpiba2 * geo.hg
+        c2v[is1] = -fi * (g2 * c0[is1] + (fp.real + 1j * fm.imag))    # :666-667
+        if is2 is not None:
+            c2v[is2] = -fip1 * (g2 * c0[is2] + (fp.imag - 1j * fm.real))   # :668-670
+    return c2 + c2v                                                   # :717
+
+
+def e_test(geo: Geometry, rho_out, vpot, omega):
+    """The synthetic "total energy" used for the 1e-9 Ha criterion:
+    E_test = ekin + (Omega/N) * sum_r V(r) rho(r)."""
+    n1, n2, n3 = geo.nr
+    return rho_out["ekin"] + omega / float(n1 * n2 * n3) * float(np.dot(vpot, rho_out["rhoe"]))
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs — oracle-side copy, cross-checked against cpmd_b200.synthetic
+# ----------------------------------------------------------------------------------------------
+
+def synthetic_inputs(geo: Geometry, nstate, seed=None, f_pattern="all2"):
+    n1, n2, n3 = geo.nr
+    n = n1
+    if seed is None:
+        seed = 1234 + n + 7 * nstate
+    rng = np.random.default_rng(seed)
+    gcutw = (min(geo.nr) / 4.0) ** 2
+    damp = np.exp(-geo.hg / (0.25 * gcutw))
+    c0 = np.empty((nstate, geo.ngw), dtype=np.complex128)
+    for i in range(nstate):
+        re = rng.standard_normal(geo.ngw)
+        im = rng.standard_normal(geo.ngw)
+        c = (re + 1j * im) * damp
+        if geo.geq0:
+            c[0] = c[0].real
+        c /= np.sqrt(dotp(geo, c, c))
+        c0[i] = c
+    f = np.full(nstate, 2.0)
+    if f_pattern == "mixed":
+        f[::3] = 1.0
+        f[1::5] = 0.0
+    v = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
+    v[:n3, :n2, :n1] = -rng.random((n3, n2, n1))
+    return c0, f, v.reshape(-1)
