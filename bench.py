@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""Benchmark of the vpsi + rhoofr hot path (BASELINE.json metric: band-FFTs/s, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--mesh 192] [--states 512] [--batch 16]
+
+One "step" = one Car-Parrinello electronic step of the hot path over all states:
+rhoofr (all pairs) -> cp_grp_redist(rho) [N>1] -> V broadcast [N>1] -> vpsi (all pairs);
+vofrho is excluded.  3*nstate band-FFTs per step.  Default workload = BASELINE.json
+configs[3], the configuration the north_star metric is quoted on (128 H2O: 192^3 mesh, 512 states
+= 256 double-packed FFTs); it fits one B200.  N>1: states sharded over GPUs per part_1d
+(CP_GROUPS), total work fixed -> "strong" scaling, as the north_star target (>=6x at 8 GPUs) is.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM when the
+timed region starts); `e2e` is the same step through the host-pointer C ABI (the entry points
+the Fortran shim binds) with pinned host buffers, H2D/D2H inside the timed region.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/staged_oracle.c,
+kind "port": the reference cannot be built in this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "band-FFTs/s in vpsi+rhoofr (FP64)"
+UNIT = "band-FFTs/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _byte_model(info, nstate):
+    """Algorithmic bytes (SURVEY 8d / DESIGN.md): C=16 ngw, S_x=16 n1 rays, S_y=16 n1 n2 zband."""
+    n1, n2, n3 = info["nr"]
+    C = 16.0 * info["ngw"]
+    Sx = 16.0 * n1 * info["nrays"]
+    Sy = 16.0 * n1 * n2 * info["zband"]
+    N8 = 8.0 * n1 * n2 * n3
+    npairs = (nstate + 1) // 2
+    rho = npairs * (2 * C + 2 * Sx + 2 * Sy) + N8
+    vps = npairs * (6 * C + 4 * Sx + 4 * Sy) + N8
+    return dict(C=C, Sx=Sx, Sy=Sy, N8=N8, rhoofr=rho, vpsi=vps, step=rho + vps)
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the CPU restatement of fftnew's staged algorithm on the host cores."""
+    if rank != 0:
+        return
+    from oracle import cpmd_oracle as orc
+    from oracle import staged
+
+    cores = staged.set_threads(0)
+    n = args.mesh
+    sample_states = args.ref_sample_states
+    geo = orc.make_geometry(n)
+    c0, f, v = orc.synthetic_inputs(geo, sample_states, seed=1234 + n + 7 * args.states)
+    c2 = np.zeros_like(c0)
+
+    def step():
+        staged.rhoofr(geo, c0, f, 1.0, 1.0)
+        staged.vpsi(geo, c0, c2, f, v, 1.0)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 3.0 * sample_states / dt
+    sample = f"{sample_states} of {args.states} states ({(sample_states + 1) // 2} packed pairs), mesh {n}^3, rhoofr+vpsi"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(args, n_gpus=args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(args, n_gpus):
+    return {"workload": f"BASELINE.json configs[3]: 128 H2O CP-MD, {args.states} states "
+                        f"({(args.states + 1) // 2} double-packed FFTs), {args.mesh}^3 mesh, dual 4",
+            "mesh": args.mesh, "states": args.states, "pairs_per_batch": args.batch,
+            "parallelism": f"cp_groups{n_gpus} (states sharded, rho allreduce, V broadcast)",
+            "l2": "inputs larger than L2 (c0 block + intermediates >> 126 MB per step)"}
+
+
+def cpu_baseline(args):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
+    from oracle import cpmd_oracle as orc
+    from oracle import staged
+
+    cores = staged.set_threads(0)
+    n = args.mesh
+    ns = args.ref_sample_states
+    geo = orc.make_geometry(n)
+    c0, f, v = orc.synthetic_inputs(geo, ns, seed=1234 + n + 7 * args.states)
+    c2 = np.zeros_like(c0)
+    staged.rhoofr(geo, c0[:2], f[:2], 1.0, 1.0)   # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    staged.rhoofr(geo, c0, f, 1.0, 1.0)
+    staged.vpsi(geo, c0, c2, f, v, 1.0)
+    dt = time.perf_counter() - t0
+    return {"value": 3.0 * ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ns} of {args.states} states, mesh {n}^3, rhoofr+vpsi once ({dt:.1f} s)"}
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    from cpmd_b200 import Plan, dist as cdist, lib, synthetic
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n, nstate = args.mesh, args.states
+    first, cnt = cdist.state_block(nstate, rank, world)
+
+    # ---- synthetic inputs: every rank generates the same data, keeps its block of states
+    d = synthetic.make_inputs(n, nstate)
+    f = d["f"]
+    plan = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], device=local, max_batch=args.batch)
+    info = plan.info
+    c0_block_host = torch.from_numpy(d["c0"][first:first + cnt]).pin_memory()
+    c2_block_host = torch.zeros_like(c0_block_host).pin_memory()
+    v_host = torch.from_numpy(d["vpot"]).pin_memory()
+    rho_host = torch.empty(plan.nnr1, dtype=torch.float64).pin_memory()
+    del d["c0"]
+    f_block = np.ascontiguousarray(f[first:first + cnt])
+
+    c0 = c0_block_host.to(dev)
+    c2 = torch.zeros_like(c0)
+    v = v_host.to(dev) if rank == 0 else torch.zeros(plan.nnr1, dtype=torch.float64, device=dev)
+    rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        # rhoofr on the rank's block (local indices: the block is a contiguous state range)
+        ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
+        if world > 1:
+            cdist.cp_grp_redist(rho)                   # rhoofr_utils.mod.F90:457-461
+            cdist.bcast_potential(v, src=0)            # V(r) once per step
+        plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
+        return ek, rg, rr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps
+
+    # ---- device-resident timing (value), with per-kernel CUDA-event timing for the roofline
+    sampler = ClockSampler(local) if rank == 0 else None
+    plan.set_profiling(True)
+    for _ in range(args.warmup):
+        step_device()
+    plan.kernel_times(reset=True)
+    l0 = plan.launch_count
+    ms_step = timed(step_device, args.steps, 0)
+    launches = plan.launch_count - l0
+    ktimes = plan.kernel_times(reset=True)
+    plan.set_profiling(False)
+    clocks = sampler.stop() if sampler else None
+    value = 3.0 * nstate / (ms_step * 1e-3)
+
+    # ---- e2e through the host-pointer C ABI (what the Fortran shim binds)
+    def step_host():
+        plan.rhoofr(c0_block_host, f_block, rho_host, flags=lib.CPB_C0_KEEP)
+        if world > 1:
+            rho.copy_(rho_host, non_blocking=True)
+            cdist.cp_grp_redist(rho)
+            rho_host.copy_(rho, non_blocking=True)
+            torch.cuda.synchronize()
+        plan.vpsi(c0_block_host, c2_block_host, f_block, v_host, flags=lib.CPB_C0_REUSE)
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ms_e2e = timed(step_host, e2e_steps, 1)
+    blk_bytes = cnt * plan.ngw * 16
+    h2d = blk_bytes * 2 + plan.nnr1 * 8          # c0 block (once, kept for vpsi) + c2 block (+=) + V
+    d2h = blk_bytes + plan.nnr1 * 8              # c2 block + rho
+    if world > 1:
+        h2d += plan.nnr1 * 8
+        d2h += plan.nnr1 * 8
+    e2e_value = 3.0 * nstate / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (largest share of the step)
+    peak, peak_src = _peaks()
+    bm = _byte_model(info, cnt)
+    dom = max(("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd"), key=lambda k: ktimes[k][0])
+    tot_ms = sum(v_[0] for v_ in ktimes.values())
+    dom_ms, dom_n = ktimes[dom]
+    npairs_local = (cnt + 1) // 2
+    pairs_per_launch = npairs_local * args.steps / max(dom_n, 1) * (2 if dom in ("x_inv", "y_inv") else 1)
+    per_pair = {"x_inv": 2 * bm["C"] + bm["Sx"], "y_inv": bm["Sx"] + bm["Sy"], "z_rho": bm["Sy"],
+                "z_vpsi": 2 * bm["Sy"], "y_fwd": bm["Sy"] + bm["Sx"], "x_fwd": bm["Sx"] + 4 * bm["C"]}[dom]
+    per_launch_extra = bm["N8"] if dom in ("z_rho", "z_vpsi") else 0.0
+    bytes_per_launch = pairs_per_launch * per_pair + per_launch_extra
+    achieved = bytes_per_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
+    step_bytes = _byte_model(info, nstate)["step"] / world
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e, "steps": e2e_steps,
+                "api": "cpb_rhoofr(CPB_C0_KEEP) + cpb_vpsi(CPB_C0_REUSE), pinned host buffers, c2 += semantics"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms / max(dom_n, 1),
+                     "kernel_share_of_step": dom_ms / max(tot_ms, 1e-9),
+                     "step_algorithmic_GB": step_bytes / 1e9,
+                     "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                     "kernel_ms_per_step": {k: v_[0] / args.steps for k, v_ in ktimes.items()}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", type=int, default=192)
+    ap.add_argument("--states", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sample-states", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        from cpmd_b200 import dist as cdist
+        cdist.init_from_env()
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

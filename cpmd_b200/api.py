@@ -120,6 +120,17 @@ class Plan:
     def launch_count(self):
         return int(self._L.cpb_plan_launch_count(self._h))
 
+    def set_profiling(self, on=True):
+        self._check(self._L.cpb_plan_set_profiling(self._h, int(bool(on))))
+
+    def kernel_times(self, reset=False):
+        """{kernel class: (total ms, launches)} accumulated while profiling was on."""
+        n = len(_lib.KERNEL_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_long * n)()
+        self._check(self._L.cpb_plan_get_kernel_times(self._h, ms, cnt, int(bool(reset))))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_KINDS)}
+
     def _c0_args(self, c0, nstate):
         if c0.ndim != 2:
             raise ValueError("c0 must be (nstate, ld)")

@@ -106,6 +106,16 @@ struct cpb_plan {
   int c0_key_nstate = 0, c0_key_ngroups = 0, c0_key_group = 0;
   bool c0_valid = false;
   long launches = 0;
+  // optional per-kernel-class timing (cpb_plan_set_profiling): CUDA events around every launch
+  bool profiling = false;
+  struct Span {
+    rt::event_t a, b;
+    int kind;
+  };
+  std::vector<Span> spans;     // recorded in the current call
+  std::vector<rt::event_t> ev_pool;
+  double kind_ms[CPB_NKINDS] = {0};
+  long kind_count[CPB_NKINDS] = {0};
 
   size_t nnr1() const { return (size_t)kr[0] * kr[1] * kr[2]; }
 };
@@ -137,6 +147,11 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_c0);
   rt::dfree(p->d_c2);
   rt::dfree(p->d_real);
+  for (auto& sp : p->spans) {
+    rt::event_destroy(sp.a);
+    rt::event_destroy(sp.b);
+  }
+  for (auto e : p->ev_pool) rt::event_destroy(e);
   for (auto e : p->ev_in) rt::event_destroy(e);
   for (auto e : p->ev_done) rt::event_destroy(e);
   rt::stream_destroy(p->s_main);
@@ -228,6 +243,48 @@ PairDev offset_pairs(const PairDev& b, int off) {
 
 constexpr int kSumBlocks = 592;  // 4 x 148 SMs
 
+rt::event_t pool_event(cpb_plan* p) {
+  if (!p->ev_pool.empty()) {
+    rt::event_t e = p->ev_pool.back();
+    p->ev_pool.pop_back();
+    return e;
+  }
+  return rt::timing_event_create();
+}
+
+// RAII: brackets one kernel launch with events when profiling is on
+struct Timed {
+  cpb_plan* p;
+  cudaStream_t st;
+  int kind;
+  rt::event_t a = nullptr;
+  Timed(cpb_plan* p_, cudaStream_t st_, int kind_) : p(p_), st(st_), kind(kind_) {
+    p->launches += 1;
+    if (p->profiling) {
+      a = pool_event(p);
+      rt::event_record(a, st);
+    }
+  }
+  ~Timed() {
+    if (p->profiling) {
+      rt::event_t b = pool_event(p);
+      rt::event_record(b, st);
+      p->spans.push_back({a, b, kind});
+    }
+  }
+};
+
+// after the stream has been synchronised: fold the recorded spans into the per-kind totals
+void resolve_spans(cpb_plan* p) {
+  for (auto& s : p->spans) {
+    p->kind_ms[s.kind] += rt::event_elapsed_ms(s.a, s.b);
+    p->kind_count[s.kind] += 1;
+    p->ev_pool.push_back(s.a);
+    p->ev_pool.push_back(s.b);
+  }
+  p->spans.clear();
+}
+
 // ------------------------------------------------------------------------------------------
 // device-resident rhoofr over an explicit pair list (states are columns of c0 with stride ldc)
 // `gate`, if non-null, is called before the kernels of batch b are enqueued (host API: wait for
@@ -249,10 +306,9 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const std::vector<PairHos
     const int nb = std::min(p->max_batch, np - off);
     if (hooks) hooks->before_batch(b, off, nb);
     PairDev prb = offset_pairs(pr, off);
-    p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb);
-    p->ky->y_inv(st, p->T1, p->T2, p->pd, nb);
-    p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb);
-    p->launches += 3;
+    { Timed t(p, st, CPB_K_X_INV); p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb); }
+    { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb); }
+    { Timed t(p, st, CPB_K_Z_RHO); p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb); }
     if (hooks) hooks->after_batch(b, off, nb);
   }
   rt::check_last("rhoofr kernels");
@@ -268,12 +324,11 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector
     const int nb = std::min(p->max_batch, np - off);
     if (hooks) hooks->before_batch(b, off, nb);
     PairDev prb = offset_pairs(pr, off);
-    p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb);
-    p->ky->y_inv(st, p->T1, p->T2, p->pd, nb);
-    p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb);
-    p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb);
-    p->kx->x_fwd(st, p->T1, c0, c2, ldc, p->pd, prb, nb, accumulate);
-    p->launches += 5;
+    { Timed t(p, st, CPB_K_X_INV); p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb); }
+    { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb); }
+    { Timed t(p, st, CPB_K_Z_VPSI); p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb); }
+    { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb); }
+    { Timed t(p, st, CPB_K_X_FWD); p->kx->x_fwd(st, p->T1, c0, c2, ldc, p->pd, prb, nb, accumulate); }
     if (hooks) hooks->after_batch(b, off, nb);
   }
   rt::check_last("vpsi kernels");
@@ -283,15 +338,15 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector
 void launch_kin(cpb_plan* p, const cplx* c0, long ldc, int first, int count, cudaStream_t st) {
   if (count <= 0) return;
   auto k = k_kin_energy;
+  Timed t(p, st, CPB_K_KIN);
   CPB_LAUNCH(k, dim3(count), dim3(256), 2 * 256 * sizeof(double), st, c0, ldc, first, p->ngw, p->geq0,
              (const double*)p->d_hg, p->d_red);
-  p->launches += 1;
 }
 
 void launch_sum(cpb_plan* p, const double* a, size_t n, double* out, cudaStream_t st) {
   auto k = k_sum;
+  Timed t(p, st, CPB_K_SUM);
   CPB_LAUNCH(k, dim3(kSumBlocks), dim3(256), 256 * sizeof(double), st, a, n, out);
-  p->launches += 1;
 }
 
 void vpsi_coefs(const std::vector<PairHost>& pairs, const double* f, bool tksham, std::vector<double>& fi,
@@ -669,6 +724,25 @@ int cpb_plan_get_maps(const cpb_plan* p, int32_t* nzhs, int32_t* indzs) {
 
 long cpb_plan_launch_count(const cpb_plan* p) { return p ? p->launches : 0; }
 
+int cpb_plan_set_profiling(cpb_plan* p, int on) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  p->profiling = on != 0;
+  return CPB_OK;
+}
+
+int cpb_plan_get_kernel_times(cpb_plan* p, double* ms, long* counts, int reset) {
+  if (!p || !ms || !counts) return fail(CPB_ERR_INVALID, "null argument");
+  for (int k = 0; k < CPB_NKINDS; ++k) {
+    ms[k] = p->kind_ms[k];
+    counts[k] = p->kind_count[k];
+    if (reset) {
+      p->kind_ms[k] = 0.0;
+      p->kind_count[k] = 0;
+    }
+  }
+  return CPB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ---------------------------------------------------------------------------------------------
@@ -693,6 +767,7 @@ int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, cons
     launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + 2 * nblk, st);  // :607-619
     rt::d2h(p->h_red, p->d_red, (size_t)(2 * nblk + kSumBlocks) * sizeof(double), st);
     rt::sync(st);
+    resolve_spans(p);
     double rg = 0, rr = 0;
     finish_rho_scalars(p, f, first, nblk, ekin, &rg, &rr);
     if (rsum_g) *rsum_g = rg;
@@ -720,6 +795,7 @@ int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nst
     run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, pairs, fi, fip1, vpot_dev,
              !(flags & CPB_VPSI_OVERWRITE), st, nullptr);
     rt::sync(st);
+    resolve_spans(p);
     return CPB_OK;
   } catch (const Error& e) {
     return fail(e.code, e.what());

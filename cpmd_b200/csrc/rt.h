@@ -44,6 +44,8 @@ inline void event_destroy(event_t) {}
 inline void event_record(event_t, cudaStream_t) {}
 inline void stream_wait(cudaStream_t, event_t) {}
 inline void event_sync(event_t) {}
+inline event_t timing_event_create() { return nullptr; }
+inline double event_elapsed_ms(event_t, event_t) { return 0.0; }
 
 #else
 
@@ -107,6 +109,16 @@ inline void event_destroy(event_t e) {
 inline void event_record(event_t e, cudaStream_t s) { ck(cudaEventRecord(e, s), "cudaEventRecord"); }
 inline void stream_wait(cudaStream_t s, event_t e) { ck(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
 inline void event_sync(event_t e) { ck(cudaEventSynchronize(e), "cudaEventSynchronize"); }
+inline event_t timing_event_create() {
+  cudaEvent_t e;
+  ck(cudaEventCreate(&e), "cudaEventCreate");
+  return e;
+}
+inline double event_elapsed_ms(event_t a, event_t b) {
+  float ms = 0.f;
+  ck(cudaEventElapsedTime(&ms, a, b), "cudaEventElapsedTime");
+  return (double)ms;
+}
 
 #endif
 

@@ -66,7 +66,11 @@ SYMBOLS = {
     "cpb_vpsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
+    "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
 }
+
+KERNEL_KINDS = ("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd", "kin_energy", "rho_sum")
 
 
 def declare(cdll: C.CDLL) -> C.CDLL:

@@ -136,6 +136,25 @@ int cpb_vpsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int 
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);
 
+/* Per-kernel-class device timing: when profiling is on, every launch is bracketed by CUDA events
+ * on its stream; totals (ms) and launch counts are accumulated per class.  Used by bench.py for
+ * the roofline of the dominant kernel; the counterpart of the reference's tiset/tihalt timers
+ * around invfftn/fwfftn/vpsi/rhoofr (timer.mod.F90:39-233). */
+enum {
+  CPB_K_X_INV = 0, /* scatter + x inverse      */
+  CPB_K_Y_INV = 1,
+  CPB_K_Z_RHO = 2, /* z inverse + density      */
+  CPB_K_Z_VPSI = 3, /* z inverse * V * z forward */
+  CPB_K_Y_FWD = 4,
+  CPB_K_X_FWD = 5, /* x forward + unpack + c2  */
+  CPB_K_KIN = 6,
+  CPB_K_SUM = 7,
+  CPB_NKINDS = 8
+};
+int cpb_plan_set_profiling(cpb_plan* plan, int on);
+int cpb_plan_get_kernel_times(cpb_plan* plan, double* ms /*[CPB_NKINDS]*/, long* counts /*[CPB_NKINDS]*/,
+                              int reset);
+
 #ifdef __cplusplus
 }
 #endif

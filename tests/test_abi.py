@@ -1,0 +1,66 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol include/cpb200.h declares,
+host-only entry points behave, and the product loader has no fallback."""
+import os
+import re
+
+import pytest
+
+from cpmd_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "cpb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    for name in _declared():
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.cpb_version()
+
+
+def test_host_only_entry_points():
+    L = lib.load()
+    for n in (16, 64, 72, 120, 128, 192, 256, 320):
+        assert L.cpb_length_supported(n) == 1
+    assert L.cpb_length_supported(22) == 0
+    # part_1d.mod.F90:22-57
+    got = []
+    for g in range(3):
+        cnt = L.cpb_part_1d_nbr_el_in_blk(10, g, 3)
+        got += [L.cpb_part_1d_get_el_in_blk(i, 10, g, 3) for i in range(1, cnt + 1)]
+    assert got == list(range(1, 11))
+
+
+def test_sizes_def_matches_registry():
+    src = open(os.path.join(ROOT, "cpmd_b200", "csrc", "sizes.def")).read()
+    L = lib.load()
+    for n, r1, r2 in re.findall(r"^CPB_SIZE\((\d+),\s*(\d+),\s*(\d+)\)", src, flags=re.M):
+        assert int(r1) * int(r2) == int(n)
+        assert L.cpb_length_supported(int(n)) == 1
+
+
+def test_no_cpu_fallback(monkeypatch, tmp_path):
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(lib.LibraryNotBuilt):
+        lib.load()
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under cpmd_b200/ may reference oracle/ or the simulator."""
+    pk = os.path.join(ROOT, "cpmd_b200")
+    for dp, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".inc", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "libcpb200_emu" not in txt or f == "cpb_defs.h", f

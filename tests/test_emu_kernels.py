@@ -1,0 +1,195 @@
+"""The CUDA kernel sources, compiled for the CPU functional simulator (tests/emu), against the
+oracle.  This is how kernel index arithmetic and the host-side plan/pipeline logic are checked
+where no GPU exists; the same comparisons run on the real device in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from cpmd_b200 import lib, synthetic
+from cpmd_b200.api import CpbError, CpmdContext, Plan, StopGM
+from helpers import ETOL, RTOL, golden_cases, load_golden, relmax
+from oracle import cpmd_oracle as orc
+
+
+def _plan(d, cdll, **kw):
+    return Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], _cdll=cdll, **kw)
+
+
+@pytest.mark.parametrize("n,nstate,mb,fp", [(16, 4, 16, "all2"), (20, 5, 2, "mixed"), (24, 7, 2, "mixed"),
+                                            (30, 6, 1, "mixed"), (36, 3, 16, "all2"), (40, 2, 16, "all2"),
+                                            (48, 4, 3, "all2"), (60, 2, 16, "all2")])
+def test_kernels_match_oracle(emu_cdll, n, nstate, mb, fp):
+    d = synthetic.make_inputs(n, nstate, f_pattern=fp)
+    geo = orc.make_geometry(n)
+    p = _plan(d, emu_cdll, max_batch=mb)
+    nz, iz = p.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)
+    info = p.info
+    assert info["nrays"] == geo.nrays and info["zband"] == geo.kr3max - geo.kr3min + 1
+    rho, ekin, rg, rr = p.rhoofr(d["c0"], d["f"])
+    ref = orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rho, ref["rhoe"]) < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL and abs(rg - ref["rsum_g"]) < ETOL and abs(rr - ref["rsum_r"]) < ETOL
+    c2 = 0.5 * d["c0"]
+    c2_ref = orc.vpsi(geo, d["c0"], c2, d["f"], d["vpot"], 1.0)
+    p.vpsi(d["c0"], c2, d["f"], d["vpot"])
+    assert relmax(c2, c2_ref) < RTOL
+    # pads of rho are exactly zero
+    r3 = rho.reshape(p.kr[2], p.kr[1], p.kr[0])
+    assert not r3[n:].any() and not r3[:, n:].any() and not r3[:, :, n:].any()
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_kernels_match_golden(emu_cdll, path):
+    d = load_golden(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2, _cdll=emu_cdll)
+    rho, ekin, rg, rr = p.rhoofr(d["c0"], d["f"], ngroups=d["ngroups"], my_group=d["group"])
+    assert relmax(rho, d["rhoe"]) < RTOL
+    if d["ngroups"] == 1:
+        assert abs(ekin - d["ekin"]) < ETOL and abs(rg - d["rsum_g"]) < ETOL
+    assert abs(rr - d["rsum_r"]) < ETOL
+    c2 = d["c2_in"].copy()
+    p.vpsi(d["c0"], c2, d["f"], d["vpot"], ngroups=d["ngroups"], my_group=d["group"])
+    assert relmax(c2, d["c2_out"]) < RTOL
+
+
+def test_overwrite_tksham_and_leading_dimension(emu_cdll):
+    n, ns = 16, 5
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    p = _plan(d, emu_cdll, max_batch=2)
+    ld = geo.ngw + 7                       # ld > ngw as in c0(nkpt%ngwk, nstate)
+    c0 = np.zeros((ns, ld), complex)
+    c0[:, :geo.ngw] = d["c0"]
+    c2 = np.full((ns, ld), 3.0 + 1j)
+    p.vpsi(c0, c2, d["f"], d["vpot"], flags=lib.CPB_VPSI_OVERWRITE | lib.CPB_VPSI_TKSHAM)
+    ref = orc.vpsi(geo, d["c0"], np.zeros_like(d["c0"]), d["f"], d["vpot"], 1.0, tksham=True)
+    assert relmax(c2[:, :geo.ngw], ref) < RTOL
+    assert np.all(c2[:, geo.ngw:] == 3.0 + 1j)          # padding rows untouched
+    rho, *_ = p.rhoofr(c0, d["f"])
+    assert relmax(rho, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+
+
+def test_groups_sum_to_full_and_c0_cache(emu_cdll):
+    n, ns = 20, 7
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    p = _plan(d, emu_cdll, max_batch=2)
+    full = orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    c2_full = orc.vpsi(geo, d["c0"], np.zeros_like(d["c0"]), d["f"], d["vpot"], 1.0)
+    acc = np.zeros(p.nnr1)
+    sums = np.zeros(3)
+    c2 = np.zeros_like(d["c0"])
+    for grp in range(3):
+        rho, ekin, rg, rr = p.rhoofr(d["c0"], d["f"], ngroups=3, my_group=grp, flags=lib.CPB_C0_KEEP)
+        acc += rho
+        sums += (ekin, rg, rr)
+        p.vpsi(d["c0"], c2, d["f"], d["vpot"], ngroups=3, my_group=grp, flags=lib.CPB_C0_REUSE)
+    assert relmax(acc, full["rhoe"]) < RTOL
+    assert np.abs(sums - (full["ekin"], full["rsum_g"], full["rsum_r"])).max() < ETOL
+    assert relmax(c2, c2_full) < RTOL
+    # a stale cache key must not be reused for a different array
+    other = d["c0"] * 2.0
+    rho2, *_ = p.rhoofr(other, d["f"], flags=lib.CPB_C0_REUSE)
+    assert relmax(rho2, 4.0 * full["rhoe"]) < RTOL
+
+
+def test_anisotropic_mesh(emu_cdll):
+    nr = (16, 20, 24)
+    geo = orc.make_geometry(nr)
+    c0, f, v = orc.synthetic_inputs(geo, 3)
+    p = Plan(nr, geo.inyh, geo.hg, 1.0, 1.0, max_batch=2, _cdll=emu_cdll)
+    rho, *_ = p.rhoofr(c0, f)
+    assert relmax(rho, orc.rhoofr(geo, c0, f, 1.0, 1.0)["rhoe"]) < RTOL
+    c2 = np.zeros_like(c0)
+    p.vpsi(c0, c2, f, v)
+    assert relmax(c2, orc.vpsi(geo, c0, np.zeros_like(c0), f, v, 1.0)) < RTOL
+
+
+def test_shuffled_g_order(emu_cdll):
+    """Neither routine depends on the order inside a |G|^2 shell: permuting the
+    plane waves (G=0 kept first) permutes c2 and leaves rho unchanged."""
+    n, ns = 16, 4
+    d = synthetic.make_inputs(n, ns)
+    rng = np.random.default_rng(7)
+    perm = np.concatenate([[0], 1 + rng.permutation(d["hg"].shape[0] - 1)])
+    p0 = _plan(d, emu_cdll)
+    p1 = Plan(d["nr"], d["inyh"][:, perm], d["hg"][perm], 1.0, 1.0, _cdll=emu_cdll)
+    c0p = np.ascontiguousarray(d["c0"][:, perm])
+    r0, *_ = p0.rhoofr(d["c0"], d["f"])
+    r1, *_ = p1.rhoofr(c0p, d["f"])
+    assert relmax(r1, r0) < RTOL
+    a = np.zeros_like(d["c0"])
+    b = np.zeros_like(d["c0"])
+    p0.vpsi(d["c0"], a, d["f"], d["vpot"])
+    p1.vpsi(c0p, b, d["f"], d["vpot"])
+    assert relmax(b, a[:, perm]) < RTOL
+
+
+def test_empty_and_single_state(emu_cdll):
+    d = synthetic.make_inputs(16, 1)
+    geo = orc.make_geometry(16)
+    p = _plan(d, emu_cdll)
+    rho, ekin, rg, rr = p.rhoofr(d["c0"], d["f"])
+    assert relmax(rho, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+    # a group that owns no state (nstate < ngroups): rho = 0, scalars = 0
+    rho, ekin, rg, rr = p.rhoofr(d["c0"], d["f"], ngroups=2, my_group=1)
+    assert not rho.any() and ekin == 0.0 and rg == 0.0 and rr == 0.0
+    c2 = np.ones_like(d["c0"])
+    p.vpsi(d["c0"], c2, d["f"], d["vpot"], ngroups=2, my_group=1)
+    assert np.all(c2 == 1.0)
+    # all occupations zero: every pair is skipped in rhoofr (rhoofr_utils.mod.F90:312-316)
+    rho, ekin, rg, rr = p.rhoofr(d["c0"], np.zeros(1))
+    assert not rho.any() and ekin == 0.0
+
+
+def test_error_paths(emu_cdll):
+    d = synthetic.make_inputs(16, 2)
+    with pytest.raises(CpbError) as e:
+        Plan((22, 22, 22), d["inyh"], d["hg"], _cdll=emu_cdll)          # no kernel for 22
+    assert e.value.code == lib.CPB_ERR_UNSUPPORTED
+    bad = d["inyh"].copy()
+    bad[0, 5] = 1                                                        # mirror falls outside the mesh
+    with pytest.raises(CpbError) as e:
+        Plan(d["nr"], bad, d["hg"], _cdll=emu_cdll)
+    assert e.value.code == lib.CPB_ERR_INVALID
+    dup = d["inyh"].copy()
+    dup[:, 9] = dup[:, 8]
+    with pytest.raises(CpbError):
+        Plan(d["nr"], dup, d["hg"], _cdll=emu_cdll)
+    both = d["inyh"].copy()
+    both[:, 9] = 2 * 9 - both[:, 8]                                      # -G of entry 8
+    with pytest.raises(CpbError):
+        Plan(d["nr"], both, d["hg"], _cdll=emu_cdll)
+    p = _plan(d, emu_cdll)
+    with pytest.raises(ValueError):
+        p.rhoofr(d["c0"][:, :50], d["f"])                                # ld < ngw
+    with pytest.raises(CpbError):
+        p.rhoofr(d["c0"], d["f"], ngroups=2, my_group=2)
+
+
+def test_context_mirrors_reference_signatures(emu_cdll):
+    n, ns = 16, 4
+    d = synthetic.make_inputs(n, ns)
+    geo = orc.make_geometry(n)
+    ctx = CpmdContext(nr=d["nr"], inyh=d["inyh"], hg=d["hg"], f=d["f"], _cdll=emu_cdll)
+    rhoe = np.zeros((ctx.nnr1, 1))
+    psi = np.zeros(1, complex)
+    ctx.rhoofr(d["c0"], rhoe, psi, ns)
+    ref = orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rhoe[:, 0], ref["rhoe"]) < RTOL and abs(ctx.ekin - ref["ekin"]) < ETOL
+    assert abs(ctx.csumg - ctx.csumr) < 1e-10
+    c2 = np.zeros_like(d["c0"])
+    ctx.vpsi(d["c0"], c2, d["f"], d["vpot"].reshape(-1, 1), psi, ns, 1, 1, False)
+    assert relmax(c2, orc.vpsi(geo, d["c0"], np.zeros_like(c2), d["f"], d["vpot"], 1.0)) < RTOL
+    # unsupported variants stop like the reference
+    with pytest.raises(StopGM):
+        ctx.vpsi(d["c0"], c2, d["f"], d["vpot"], psi, ns, ikind=2)
+    ctx.tlsd = True
+    with pytest.raises(StopGM):
+        ctx.rhoofr(d["c0"], rhoe, psi, ns)
+    ctx.tlsd = False
+    # charge check (rhoofr_utils.mod.F90:625-635): a non-normalisable input still passes the
+    # identity, so provoke it by lying about omega-independent sums via delta
+    ctx.delta = -1.0
+    with pytest.raises(StopGM):
+        ctx.rhoofr(d["c0"], rhoe, psi, ns)

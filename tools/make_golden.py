@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz: small input/output vectors of the hot path.
+
+The reference (CPMD 4.3, Fortran + FFTW + MPI) cannot be built or imported in this container and
+ships no fixtures for vpsi/rhoofr, so these vectors come from oracle/cpmd_oracle.py (the NumPy
+restatement, itself pinned by tests/test_oracle.py's known-answer tests and cross-checked against
+oracle/staged_oracle.c).  They freeze the oracle: any later change of its numerics shows up as a
+diff against these files.  PARITY UNPINNED with respect to the reference's own tests.
+
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import cpmd_oracle as orc  # noqa: E402
+
+CASES = [
+    # name, mesh, nstate, f_pattern, omega, tpiba2, (group, ngroups)
+    ("n16_s5_mixed", (16, 16, 16), 5, "mixed", 1.7, 0.8, (0, 1)),
+    ("n20_s4_all2", (20, 20, 20), 4, "all2", 1.0, 1.0, (0, 1)),
+    ("n16x20x24_s3", (16, 20, 24), 3, "all2", 2.0, 1.1, (0, 1)),
+    ("n16_s7_grp1of3", (16, 16, 16), 7, "mixed", 1.0, 1.0, (1, 3)),
+]
+
+
+def main():
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    for name, nr, ns, fp, omega, tpiba2, (grp, ngrp) in CASES:
+        geo = orc.make_geometry(nr)
+        c0, f, v = orc.synthetic_inputs(geo, ns, seed=4242 + ns + nr[0], f_pattern=fp)
+        rho = orc.rhoofr(geo, c0, f, omega, tpiba2, grp, ngrp)
+        c2_in = 0.25 * c0[::-1].copy()
+        c2 = orc.vpsi(geo, c0, c2_in, f, v, tpiba2, grp, ngrp)
+        np.savez_compressed(os.path.join(out, name + ".npz"), nr=np.array(nr), inyh=geo.inyh, hg=geo.hg,
+                            nzhs=geo.nzhs, indzs=geo.indzs, c0=c0, f=f, vpot=v, omega=omega, tpiba2=tpiba2,
+                            group=grp, ngroups=ngrp, rhoe=rho["rhoe"], ekin=rho["ekin"],
+                            rsum_g=rho["rsum_g"], rsum_r=rho["rsum_r"], c2_in=c2_in, c2_out=c2)
+        print(name, "ngw", geo.ngw, "nnr1", geo.nnr1)
+
+
+if __name__ == "__main__":
+    main()
