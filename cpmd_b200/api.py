@@ -107,7 +107,8 @@ class Plan:
         return dict(nr=tuple(inf.nr), kr=tuple(inf.kr), ngw=inf.ngw, geq0=bool(inf.geq0), nrays=inf.nrays,
                     zband=inf.zband, xband=inf.xband, max_batch=inf.max_batch, device=inf.device,
                     radix=tuple((inf.radix[d][0], inf.radix[d][1]) for d in range(3)),
-                    workspace_bytes=inf.workspace_bytes)
+                    workspace_bytes=inf.workspace_bytes,
+                    band_pruned=tuple(inf.band_pruned), chunk_xtiles=inf.chunk_xtiles)
 
     def maps(self):
         """(nzhs, indzs) with the reference's numbering (fftprp_utils.mod.F90:269-285)."""

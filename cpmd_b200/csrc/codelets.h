@@ -126,6 +126,12 @@ CPB_HD void dft4(cplx (&v)[4]) {
 
 template <int R, bool INV>
 CPB_HD void dft(cplx (&v)[R]) {
+#ifdef CPB_DBG_NOFFT
+  if constexpr (R > 0) {
+    v[0].x += v[R - 1].y;
+    return;
+  }
+#endif
   if constexpr (R == 1) {
   } else if constexpr (R == 2) {
     cplx a = v[0], b = v[1];
@@ -149,6 +155,90 @@ CPB_HD void dft(cplx (&v)[R]) {
         u[k] = v[j + Rb * k];
       });
       dft<Ra, INV>(u);
+      static_for<0, Ra>([&](auto pp) {
+        constexpr int p = decltype(pp)::value;
+        t[j * Ra + p] = mul_root<R, j * p, INV>(u[p]);
+      });
+    });
+    static_for<0, Ra>([&](auto pp) {
+      constexpr int p = decltype(pp)::value;
+      cplx u[Rb];
+      static_for<0, Rb>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        u[j] = t[j * Ra + p];
+      });
+      dft<Rb, INV>(u);
+      static_for<0, Rb>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        v[p + Ra * q] = u[q];
+      });
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dft_in<R, INV, LO, HI>(v): same transform, but the caller guarantees v[k] == 0 for k outside
+// [LO, HI) (those entries are ignored, not read).  Every 1-D transform of the sparse wavefunction
+// FFT has this structure: the G-sphere only fills the middle half of each axis
+// (fftprp_utils.mod.F90:161-192), so the first radix pass sees zeros in half of its inputs.
+// Zero terms are dropped at compile time (the compiler may not fold x + 0.0 under IEEE rules).
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct LeafDirectMax {  // largest non-zero count for which the direct sum beats the butterfly
+  static constexpr int v = (R == 4) ? 2 : 1;
+};
+
+constexpr int cpb_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+constexpr int cpb_clamp(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+template <int R, bool INV, int LO, int HI>
+CPB_HD void dft_in(cplx (&v)[R]) {
+  if constexpr (LO <= 0 && HI >= R) {
+    dft<R, INV>(v);
+#ifdef CPB_DBG_NOFFT
+  } else if constexpr (R > 0) {
+    v[0].x += v[LO].y;
+    static_for<0, R>([&](auto pp) {
+      constexpr int q = decltype(pp)::value;
+      if constexpr (q < LO || q >= HI) v[q] = v[LO];
+    });
+#endif
+  } else if constexpr (HI <= LO) {
+    static_for<0, R>([&](auto pp) { v[decltype(pp)::value] = mk(0.0, 0.0); });
+  } else if constexpr (Split<R>::a == 1 || R == 4 || R == 2) {
+    if constexpr (HI - LO <= LeafDirectMax<R>::v) {
+      cplx o[R];
+      static_for<0, R>([&](auto pp) {
+        constexpr int p = decltype(pp)::value;
+        o[p] = mul_root<R, LO * p, INV>(v[LO]);
+        static_for<LO + 1, HI>([&](auto kk) {
+          constexpr int k = decltype(kk)::value;
+          o[p] = cadd(o[p], mul_root<R, k * p, INV>(v[k]));
+        });
+      });
+      static_for<0, R>([&](auto pp) { v[decltype(pp)::value] = o[decltype(pp)::value]; });
+    } else {
+      static_for<0, R>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        if constexpr (k < LO || k >= HI) v[k] = mk(0.0, 0.0);
+      });
+      dft<R, INV>(v);
+    }
+  } else {
+    constexpr int Ra = Split<R>::a;
+    constexpr int Rb = R / Ra;
+    cplx t[R];
+    static_for<0, Rb>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      // non-zero ka: LO <= j + Rb*ka < HI
+      constexpr int ka_lo = cpb_clamp(cpb_ceil_div(LO - j, Rb), 0, Ra);
+      constexpr int ka_hi = cpb_clamp(cpb_ceil_div(HI - j, Rb), 0, Ra);
+      cplx u[Ra];
+      static_for<0, Ra>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        u[k] = v[j + Rb * k];
+      });
+      dft_in<Ra, INV, ka_lo, ka_hi>(u);
       static_for<0, Ra>([&](auto pp) {
         constexpr int p = decltype(pp)::value;
         t[j * Ra + p] = mul_root<R, j * p, INV>(u[p]);

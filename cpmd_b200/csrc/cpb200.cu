@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -70,6 +71,13 @@ struct cpb_plan {
   double tpiba2 = 0, omega = 0;
   int device = 0;
   int max_batch = 16;
+  int nxt = 0;       // x tiles of B columns
+  int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
+  int n_sm = 148;
+  int x_sub = 4;          // pairs per x-pass sub-batch (their c0/c2 columns are staged in L2)
+  int x_prefetch = 1;
+  size_t t1_pair = 0;     // elements of T1 per pair
+  bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
   const AxisKernels *kx = nullptr, *ky = nullptr, *kz = nullptr;
   // geometry (host copies)
   int xlo = 0, xhi = -1, zlo = 0, nzb = 0, nrays = 0, ref_nrays = 0, ntiles = 0, nent = 0;
@@ -285,6 +293,52 @@ void resolve_spans(cpb_plan* p) {
   p->spans.clear();
 }
 
+// pairs each block of a y/z kernel loops over: as many as possible (longer prefetch pipelines)
+// while the grid still holds ~2 full waves of blocks
+int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group) {
+  const int target = 2 * p->n_sm * 3;
+  int groups = (target + blocks_per_pair_group - 1) / std::max(blocks_per_pair_group, 1);
+  groups = std::max(1, std::min(groups, npair));
+  return (npair + groups - 1) / groups;
+}
+
+
+void launch_prefetch(cpb_plan* p, const cplx* base, long ldc, const PairDev& pr, int npair, cudaStream_t st) {
+  const size_t bytes = (size_t)p->ngw * sizeof(cplx);
+  const unsigned gx = (unsigned)((bytes + 256 * (size_t)kPrefetchChunk - 1) / (256 * (size_t)kPrefetchChunk));
+  auto k = k_l2_prefetch_cols;
+  p->launches += 1;
+  CPB_LAUNCH(k, dim3(gx, 2 * npair), dim3(256), 0, st, base, ldc, pr.st1, pr.st2, npair, p->ngw);
+}
+
+// x passes in sub-batches of x_sub pairs: the sub-batch's plane-wave columns are staged in L2 by
+// sequential bulk prefetches, then gathered (c0) / read-modify-written (c2) at random from there.
+void run_x_inv(cpb_plan* p, const cplx* c0, long ldc, const PairDev& prb, int nb, cudaStream_t st) {
+  for (int o = 0; o < nb; o += p->x_sub) {
+    const int ns = std::min(p->x_sub, nb - o);
+    PairDev prs = offset_pairs(prb, o);
+    if (p->x_prefetch) launch_prefetch(p, c0, ldc, prs, ns, st);
+    Timed t(p, st, CPB_K_X_INV);
+    p->kx->x_inv(st, c0, ldc, p->T1 + (size_t)o * p->t1_pair, p->pd, prs, ns, pairs_per_group(p, ns, p->ntiles),
+                 p->half_x);
+  }
+}
+
+void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb, bool accumulate,
+               cudaStream_t st) {
+  for (int o = 0; o < nb; o += p->x_sub) {
+    const int ns = std::min(p->x_sub, nb - o);
+    PairDev prs = offset_pairs(prb, o);
+    if (p->x_prefetch) {
+      launch_prefetch(p, c0, ldc, prs, ns, st);
+      launch_prefetch(p, c2, ldc, prs, ns, st);
+    }
+    Timed t(p, st, CPB_K_X_FWD);
+    p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, c0, c2, ldc, p->pd, prs, ns,
+                 pairs_per_group(p, ns, p->ntiles), p->half_x, accumulate);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // device-resident rhoofr over an explicit pair list (states are columns of c0 with stride ldc)
 // `gate`, if non-null, is called before the kernels of batch b are enqueued (host API: wait for
@@ -306,9 +360,13 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const std::vector<PairHos
     const int nb = std::min(p->max_batch, np - off);
     if (hooks) hooks->before_batch(b, off, nb);
     PairDev prb = offset_pairs(pr, off);
-    { Timed t(p, st, CPB_K_X_INV); p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb); }
-    { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb); }
-    { Timed t(p, st, CPB_K_Z_RHO); p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb); }
+    run_x_inv(p, c0, ldc, prb, nb, st);
+    // y and z passes chunk by chunk of x tiles: the chunk's T2 stays in L2
+    for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+      const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+      { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb), p->half_y); }
+      { Timed t(p, st, CPB_K_Z_RHO); p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
+    }
     if (hooks) hooks->after_batch(b, off, nb);
   }
   rt::check_last("rhoofr kernels");
@@ -324,11 +382,15 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector
     const int nb = std::min(p->max_batch, np - off);
     if (hooks) hooks->before_batch(b, off, nb);
     PairDev prb = offset_pairs(pr, off);
-    { Timed t(p, st, CPB_K_X_INV); p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb); }
-    { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb); }
-    { Timed t(p, st, CPB_K_Z_VPSI); p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb); }
-    { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb); }
-    { Timed t(p, st, CPB_K_X_FWD); p->kx->x_fwd(st, p->T1, c0, c2, ldc, p->pd, prb, nb, accumulate); }
+    run_x_inv(p, c0, ldc, prb, nb, st);
+    for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+      const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+      const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb);
+      { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      { Timed t(p, st, CPB_K_Z_VPSI); p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1]), p->half_z); }
+      { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+    }
+    run_x_fwd(p, c0, c2, ldc, prb, nb, accumulate, st);
     if (hooks) hooks->after_batch(b, off, nb);
   }
   rt::check_last("vpsi kernels");
@@ -451,7 +513,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->tpiba2 = tpiba2;
     p->omega = omega;
     p->device = device;
-    p->max_batch = max_batch_pairs > 0 ? max_batch_pairs : 16;
+    p->max_batch = std::min(max_batch_pairs > 0 ? max_batch_pairs : 16, (int)kMaxGroup);
     p->kx = find_axis_kernels(nr[0]);
     p->ky = find_axis_kernels(nr[1]);
     p->kz = find_axis_kernels(nr[2]);
@@ -462,7 +524,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       throw Error(CPB_ERR_UNSUPPORTED, buf);
     }
     const int n1 = nr[0], n2 = nr[1], n3 = nr[2];
-    const int SL = p->kx->sl, LD = SL + 1;
+    const int SL = p->kx->sl, LD = SL;  // XCfg::LDB
     if ((long)n1 * LD > 65535) throw Error(CPB_ERR_UNSUPPORTED, "n1 too large for 16-bit tile locations");
 
     // ---- 0-based box positions; the mirror of g is n-g (inyh -> 2*nh-inyh, fftprp :272-277)
@@ -613,8 +675,32 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       ent_ig[i] = ents[i].ig;
       ent_loc[i] = ents[i].loc;
     }
-    for (int t = 0; t < ntiles; ++t) ent_off[t + 1] += ent_off[t];
+    int max_tile_ent = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      max_tile_ent = std::max(max_tile_ent, ent_off[t + 1]);
+      ent_off[t + 1] += ent_off[t];
+    }
 
+    {
+      // band-pruned kernel variants (KRange): index band inside [r2*klo, r2*khi) of the axis
+      int ymin = n2, ymax = -1;
+      for (int zr = 0; zr < nzb; ++zr)
+        if (yhi[zr] >= ylo[zr]) {
+          ymin = std::min(ymin, ylo[zr]);
+          ymax = std::max(ymax, yhi[zr]);
+        }
+      auto fits = [](const AxisKernels* k, int lo, int hi) {
+        return lo >= k->r2 * k->klo && hi < k->r2 * k->khi;
+      };
+      p->half_x = fits(p->kx, xlo, xhi) && max_tile_ent <= p->kx->x_ept_half * p->kx->x_threads;
+      if (max_tile_ent > p->kx->x_ept_full * p->kx->x_threads)
+        throw Error(CPB_ERR_UNSUPPORTED, "x-pass tile holds more plane waves than the kernel's register budget");
+      p->half_y = fits(p->ky, ymin, ymax);
+      p->half_z = fits(p->kz, zlo, zhi);
+      if (const char* e = std::getenv("CPB_NO_HALF")) {
+        if (std::atoi(e)) p->half_x = p->half_y = p->half_z = false;
+      }
+    }
     p->xlo = xlo;
     p->xhi = xhi;
     p->zlo = zlo;
@@ -626,6 +712,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
 
     // ---- device side
     rt::set_device(device);
+    p->n_sm = rt::sm_count(device);
     p->d_ylo = upload(ylo);
     p->d_yhi = upload(yhi);
     p->d_rayoff = upload(rayoff);
@@ -637,10 +724,28 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->d_tw1 = upload(make_twiddles(n1));
     p->d_tw2 = upload(make_twiddles(n2));
     p->d_tw3 = upload(make_twiddles(n3));
-    const size_t t1 = (size_t)p->max_batch * nrays * n1 * sizeof(cplx);
-    const size_t t2 = (size_t)p->max_batch * nzb * n2 * n1 * sizeof(cplx);
+    // T1[pair][xt][ray][B]; T2[pair][xtc][y][zr][B] for one chunk of x tiles, sized so that the
+    // chunk of a whole batch stays L2-resident between the y and z passes (126 MB L2 on B200).
+    const int Bx = p->kx->b;
+    p->nxt = (n1 + Bx - 1) / Bx;
+    {
+      const size_t per_xt = (size_t)p->max_batch * n2 * nzb * Bx * sizeof(cplx);
+      size_t budget = (size_t)48 << 20;
+      if (const char* e = std::getenv("CPB_L2_CHUNK_MB")) budget = (size_t)std::max(1, std::atoi(e)) << 20;
+      p->chunk_xt = (int)std::max<size_t>(1, std::min<size_t>(p->nxt, budget / std::max<size_t>(per_xt, 1)));
+      if (const char* e = std::getenv("CPB_CHUNK_XT")) p->chunk_xt = std::max(1, std::min(p->nxt, std::atoi(e)));
+    }
+    p->t1_pair = (size_t)p->nxt * nrays * Bx;
+    if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("CPB_X_PREFETCH")) p->x_prefetch = std::atoi(e);
+    const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
+    const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
     p->T1 = (cplx*)rt::dmalloc(t1);
     p->T2 = (cplx*)rt::dmalloc(t2);
+    // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite
+    rt::dzero(p->T1, t1, 0);
+    rt::dzero(p->T2, t2, 0);
+    rt::sync(0);
     p->workspace_bytes = t1 + t2;
     p->s_main = rt::stream_create();
     p->s_in = rt::stream_create();
@@ -659,6 +764,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     pd.nzb = nzb;
     pd.nrays = nrays;
     pd.ntiles = ntiles;
+    pd.nxt = p->nxt;
     pd.ylo = p->d_ylo;
     pd.yhi = p->d_yhi;
     pd.rayoff = p->d_rayoff;
@@ -712,6 +818,10 @@ int cpb_plan_get_info(const cpb_plan* p, cpb_plan_info* info) {
     info->radix[d][1] = ks[d]->r2;
   }
   info->workspace_bytes = p->workspace_bytes;
+  info->band_pruned[0] = p->half_x;
+  info->band_pruned[1] = p->half_y;
+  info->band_pruned[2] = p->half_z;
+  info->chunk_xtiles = p->chunk_xt;
   return CPB_OK;
 }
 

@@ -20,6 +20,7 @@
 #define CPB_LAUNCH_BOUNDS(...)
 #define CPB_RESTRICT
 #define CPB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::dyn_smem())
+#define CPB_SHARED static thread_local
 #define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
   ::emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
 #else
@@ -32,6 +33,7 @@
 #define CPB_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char cpb_dyn_smem_[];   \
   type* name = reinterpret_cast<type*>(cpb_dyn_smem_)
+#define CPB_SHARED __shared__
 #define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
@@ -65,5 +67,21 @@ CPB_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + 
 // a * conj(b)
 CPB_HD cplx cmulc(cplx a, cplx b) { return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 CPB_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+
+// Cache-policy helpers.  Streaming accesses (the big intermediates that are written once and read
+// once) are marked evict-first so that they do not push the gather-heavy plane-wave columns, which
+// are staged in L2 by l2_prefetch(), out of the 126 MB L2.
+#if defined(CPB_EMULATE)
+inline void st_stream(cplx* p, cplx v) { *p = v; }
+inline cplx ld_stream(const cplx* p) { return *p; }
+inline void l2_prefetch(const void*, unsigned) {}
+#else
+CPB_D void st_stream(cplx* p, cplx v) { __stcs(p, v); }
+CPB_D cplx ld_stream(const cplx* p) { return __ldcs(p); }
+// TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned address) into L2
+CPB_D void l2_prefetch(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#endif
 
 }  // namespace cpb

@@ -57,4 +57,24 @@ CPB_GLOBAL k_sum(const double* CPB_RESTRICT a, size_t n, double* CPB_RESTRICT pa
   if (tid == 0) partial[blockIdx.x] = red[0];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stage the plane-wave columns of a group of pairs in L2 with sequential TMA bulk prefetches.
+// The x passes gather/scatter 16-byte coefficients at random positions of these columns
+// (nzhs/indzs order vs |G|^2 order); straight from HBM that access pattern is bound by the DRAM
+// row-activation rate, from L2 it is not.  grid = (ceil(ngw*16 / (256*CHUNK)), ncols), block = 256
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned kPrefetchChunk = 2048;  // bytes per thread
+
+CPB_GLOBAL k_l2_prefetch_cols(const cplx* CPB_RESTRICT base, long ldc, const int* CPB_RESTRICT st1,
+                              const int* CPB_RESTRICT st2, int npair, int ngw) {
+  const int col = blockIdx.y;  // 0 .. 2*npair-1
+  const int s = (col < npair) ? st1[col] : st2[col - npair];
+  if (s < 0) return;
+  const size_t bytes = (size_t)ngw * sizeof(cplx);
+  const size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kPrefetchChunk;
+  if (off >= bytes) return;
+  const size_t n = (bytes - off < kPrefetchChunk) ? bytes - off : kPrefetchChunk;
+  l2_prefetch(reinterpret_cast<const char*>(base + (size_t)s * ldc) + off, (unsigned)n);
+}
+
 }  // namespace cpb

@@ -21,6 +21,7 @@ namespace rt {
 
 inline void set_device(int) {}
 inline int device_count() { return 1; }
+inline int sm_count(int) { return 4; }
 inline void* dmalloc(size_t n) {
   void* p = std::malloc(n ? n : 1);
   if (!p) throw Error(-3, "out of host memory (emulated device)");
@@ -60,6 +61,11 @@ inline int device_count() {
   int n = 0;
   ck(cudaGetDeviceCount(&n), "cudaGetDeviceCount");
   return n;
+}
+inline int sm_count(int dev) {
+  int n = 0;
+  ck(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+  return n > 0 ? n : 148;
 }
 inline void* dmalloc(size_t n) {
   void* p = nullptr;

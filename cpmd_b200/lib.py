@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpb200.so")
+# CPB200_LIB: tuning hook, path of an alternative build of the same library (never a fallback)
+LIB_PATH = os.environ.get("CPB200_LIB") or os.path.join(_HERE, "libcpb200.so")
 
 # status codes / flags (include/cpb200.h)
 CPB_OK = 0
@@ -38,6 +39,8 @@ class PlanInfo(C.Structure):
         ("device", C.c_int),
         ("radix", (C.c_int * 2) * 3),
         ("workspace_bytes", C.c_size_t),
+        ("band_pruned", C.c_int * 3),
+        ("chunk_xtiles", C.c_int),
     ]
 
 

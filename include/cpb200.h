@@ -78,6 +78,8 @@ typedef struct {
   int device;
   int radix[3][2];    /* two-pass factorisation of each axis */
   size_t workspace_bytes;
+  int band_pruned[3]; /* 1: the axis runs the band-pruned kernel variants (coefficients in the middle half) */
+  int chunk_xtiles;   /* x tiles (of 8 columns) per y/z chunk; the chunk's intermediate stays in L2 */
 } cpb_plan_info;
 
 const char* cpb_last_error(void);
