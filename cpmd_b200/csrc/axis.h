@@ -10,18 +10,17 @@ namespace cpb {
 #define CPB_B 8    // batch columns (consecutive x) per block in the y/z passes: 8*16 B = 128 B rows
 #endif
 #ifndef CPB_SL
-#define CPB_SL 16  // ray slots per block in the x pass (a tile of rays plus their mirrors)
+#define CPB_SL 16  // consecutive rays per block in the x pass
 #endif
 
 struct AxisKernels {
   int n, r1, r2;
   int b, sl;
   int klo, khi;  // band-pruned k range of the first radix pass: index band must lie in [r2*klo, r2*khi)
-  // x passes: `ppg` = pairs per block (pair groups in grid.y), `half` = band-pruned instantiation
-  void (*x_inv)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&,
-                int npair, int ppg, bool half);
-  void (*x_fwd)(cudaStream_t, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev&,
-                const PairDev&, int npair, int ppg, bool half, bool accumulate);
+  // x passes on the band-ray storage G (see kernels.h): `ppg` = pairs per block (pair groups in
+  // grid.y), `half` = band-pruned instantiation
+  void (*x_inv)(cudaStream_t, const cplx* G, cplx* T1, const PlanDev&, int npair, int ppg, bool half);
+  void (*x_fwd)(cudaStream_t, const cplx* T1, cplx* G, const PlanDev&, int npair, int ppg, bool half);
   // y/z passes work on one chunk of x tiles [xt0, xt0+nxc) (T2 holds that chunk only); `half`
   // selects the band-pruned instantiation (KRange), `ppg` = pairs per block (pair groups in grid.z)
   void (*y_inv)(cudaStream_t, const cplx* T1, cplx* T2, const PlanDev&, int npair, int xt0, int nxc,
@@ -32,8 +31,7 @@ struct AxisKernels {
                 int xt0, int nxc, bool half);
   void (*z_vpsi)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
                  int ppg, bool half);
-  int yz_blocks_per_sm;
-  int x_threads, x_ept_half, x_ept_full;  // x pass: block size, plane waves per thread it can hold  // occupancy the y/z kernels are compiled for
+  int yz_blocks_per_sm;  // occupancy the y/z kernels are compiled for
 };
 
 const AxisKernels* find_axis_kernels(int n);

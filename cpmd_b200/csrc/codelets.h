@@ -126,12 +126,6 @@ CPB_HD void dft4(cplx (&v)[4]) {
 
 template <int R, bool INV>
 CPB_HD void dft(cplx (&v)[R]) {
-#ifdef CPB_DBG_NOFFT
-  if constexpr (R > 0) {
-    v[0].x += v[R - 1].y;
-    return;
-  }
-#endif
   if constexpr (R == 1) {
   } else if constexpr (R == 2) {
     cplx a = v[0], b = v[1];
@@ -188,21 +182,13 @@ struct LeafDirectMax {  // largest non-zero count for which the direct sum beats
   static constexpr int v = (R == 4) ? 2 : 1;
 };
 
-constexpr int cpb_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
-constexpr int cpb_clamp(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+CPB_HD constexpr int cpb_ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+CPB_HD constexpr int cpb_clamp(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 template <int R, bool INV, int LO, int HI>
 CPB_HD void dft_in(cplx (&v)[R]) {
   if constexpr (LO <= 0 && HI >= R) {
     dft<R, INV>(v);
-#ifdef CPB_DBG_NOFFT
-  } else if constexpr (R > 0) {
-    v[0].x += v[LO].y;
-    static_for<0, R>([&](auto pp) {
-      constexpr int q = decltype(pp)::value;
-      if constexpr (q < LO || q >= HI) v[q] = v[LO];
-    });
-#endif
   } else if constexpr (HI <= LO) {
     static_for<0, R>([&](auto pp) { v[decltype(pp)::value] = mk(0.0, 0.0); });
   } else if constexpr (Split<R>::a == 1 || R == 4 || R == 2) {

@@ -74,22 +74,23 @@ struct cpb_plan {
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
-  int x_sub = 4;          // pairs per x-pass sub-batch (their c0/c2 columns are staged in L2)
-  int x_prefetch = 1;
+  int x_sub = 4;          // pairs per x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
+  size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
   const AxisKernels *kx = nullptr, *ky = nullptr, *kz = nullptr;
   // geometry (host copies)
-  int xlo = 0, xhi = -1, zlo = 0, nzb = 0, nrays = 0, ref_nrays = 0, ntiles = 0, nent = 0;
+  int xlo = 0, xhi = -1, zlo = 0, nzb = 0, nrays = 0, ref_nrays = 0, nrp = 0;
   std::vector<int32_t> nzhs, indzs;
   // device data
   PlanDev pd;
-  int *d_ylo = nullptr, *d_yhi = nullptr, *d_rayoff = nullptr, *d_slot_ray = nullptr,
-      *d_ent_off = nullptr, *d_ent_ig = nullptr;
-  uint32_t* d_ent_loc = nullptr;
+  int *d_ylo = nullptr, *d_yhi = nullptr, *d_rayoff = nullptr;
+  uint32_t *d_gpos = nullptr, *d_gneg = nullptr;
   double* d_hg = nullptr;
   cplx *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw3 = nullptr;
   cplx *T1 = nullptr, *T2 = nullptr;
+  cplx *G = nullptr;   // band-ray storage, inverse side: non-plane-wave positions stay zero forever
+  cplx *Gf = nullptr;  // band-ray storage, forward side (fully overwritten by k_x_fwd)
   size_t workspace_bytes = 0;
   // per-call pair descriptors
   int pair_cap = 0;
@@ -135,10 +136,10 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_ylo);
   rt::dfree(p->d_yhi);
   rt::dfree(p->d_rayoff);
-  rt::dfree(p->d_slot_ray);
-  rt::dfree(p->d_ent_off);
-  rt::dfree(p->d_ent_ig);
-  rt::dfree(p->d_ent_loc);
+  rt::dfree(p->d_gpos);
+  rt::dfree(p->d_gneg);
+  rt::dfree(p->G);
+  rt::dfree(p->Gf);
   rt::dfree(p->d_hg);
   rt::dfree(p->d_tw1);
   rt::dfree(p->d_tw2);
@@ -250,6 +251,7 @@ PairDev offset_pairs(const PairDev& b, int off) {
 }
 
 constexpr int kSumBlocks = 592;  // 4 x 148 SMs
+constexpr int kRedPerState = 2 * kKinChunks;  // k_kin_energy partials per state
 
 rt::event_t pool_event(cpb_plan* p) {
   if (!p->ev_pool.empty()) {
@@ -303,23 +305,29 @@ int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group) {
 }
 
 
-void launch_prefetch(cpb_plan* p, const cplx* base, long ldc, const PairDev& pr, int npair, cudaStream_t st) {
-  const size_t bytes = (size_t)p->ngw * sizeof(cplx);
-  const unsigned gx = (unsigned)((bytes + 256 * (size_t)kPrefetchChunk - 1) / (256 * (size_t)kPrefetchChunk));
-  auto k = k_l2_prefetch_cols;
-  p->launches += 1;
-  CPB_LAUNCH(k, dim3(gx, 2 * npair), dim3(256), 0, st, base, ldc, pr.st1, pr.st2, npair, p->ngw);
+// pair groups for the elementwise G-space kernels: enough blocks to fill the machine a few times
+int ew_ppg(const cpb_plan* p, int npair) {
+  const int bx = (p->ngw + 255) / 256;
+  int groups = (8 * p->n_sm + bx - 1) / bx;
+  groups = std::max(1, std::min(groups, npair));
+  return (npair + groups - 1) / groups;
 }
 
-// x passes in sub-batches of x_sub pairs: the sub-batch's plane-wave columns are staged in L2 by
-// sequential bulk prefetches, then gathered (c0) / read-modify-written (c2) at random from there.
+// x passes in sub-batches of x_sub pairs: k_pack fills the sub-batch's band-ray storage G (it stays
+// in L2), the x FFT streams it into T1; the forward direction is the mirror with k_unpack last.
 void run_x_inv(cpb_plan* p, const cplx* c0, long ldc, const PairDev& prb, int nb, cudaStream_t st) {
   for (int o = 0; o < nb; o += p->x_sub) {
     const int ns = std::min(p->x_sub, nb - o);
     PairDev prs = offset_pairs(prb, o);
-    if (p->x_prefetch) launch_prefetch(p, c0, ldc, prs, ns, st);
+    {
+      Timed t(p, st, CPB_K_PACK);
+      const int ppg = ew_ppg(p, ns);
+      auto k = k_pack;
+      CPB_LAUNCH(k, dim3((p->ngw + 255) / 256, (ns + ppg - 1) / ppg), dim3(256), 0, st, c0, ldc, p->G, p->pd, prs,
+                 ns, ppg);
+    }
     Timed t(p, st, CPB_K_X_INV);
-    p->kx->x_inv(st, c0, ldc, p->T1 + (size_t)o * p->t1_pair, p->pd, prs, ns, pairs_per_group(p, ns, p->ntiles),
+    p->kx->x_inv(st, p->G, p->T1 + (size_t)o * p->t1_pair, p->pd, ns, pairs_per_group(p, ns, p->nrp / p->kx->sl),
                  p->half_x);
   }
 }
@@ -329,13 +337,21 @@ void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& p
   for (int o = 0; o < nb; o += p->x_sub) {
     const int ns = std::min(p->x_sub, nb - o);
     PairDev prs = offset_pairs(prb, o);
-    if (p->x_prefetch) {
-      launch_prefetch(p, c0, ldc, prs, ns, st);
-      launch_prefetch(p, c2, ldc, prs, ns, st);
+    {
+      Timed t(p, st, CPB_K_X_FWD);
+      p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, p->Gf, p->pd, ns,
+                   pairs_per_group(p, ns, p->nrp / p->kx->sl), p->half_x);
     }
-    Timed t(p, st, CPB_K_X_FWD);
-    p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, c0, c2, ldc, p->pd, prs, ns,
-                 pairs_per_group(p, ns, p->ntiles), p->half_x, accumulate);
+    Timed t(p, st, CPB_K_UNPACK);
+    const int ppg = ew_ppg(p, ns);
+    const dim3 grid((p->ngw + 255) / 256, (ns + ppg - 1) / ppg);
+    if (accumulate) {
+      auto k = k_unpack<true>;
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->Gf, c0, c2, ldc, p->pd, prs, ns, ppg);
+    } else {
+      auto k = k_unpack<false>;
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->Gf, c0, c2, ldc, p->pd, prs, ns, ppg);
+    }
   }
 }
 
@@ -396,13 +412,13 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector
   rt::check_last("vpsi kernels");
 }
 
-// kin_energy + dotp partial sums for states [first, first+count) of c0 -> d_red[0 .. 2*count)
+// kin_energy + dotp partial sums for states [first, first+count) of c0 -> d_red[0 .. kRedPerState*count)
 void launch_kin(cpb_plan* p, const cplx* c0, long ldc, int first, int count, cudaStream_t st) {
   if (count <= 0) return;
   auto k = k_kin_energy;
   Timed t(p, st, CPB_K_KIN);
-  CPB_LAUNCH(k, dim3(count), dim3(256), 2 * 256 * sizeof(double), st, c0, ldc, first, p->ngw, p->geq0,
-             (const double*)p->d_hg, p->d_red);
+  CPB_LAUNCH(k, dim3(kKinChunks, count), dim3(256), 2 * 256 * sizeof(double), st, c0, ldc, first, p->ngw,
+             p->geq0, (const double*)p->d_hg, p->d_red);
 }
 
 void launch_sum(cpb_plan* p, const double* a, size_t n, double* out, cudaStream_t st) {
@@ -440,19 +456,24 @@ void rho_coefs(cpb_plan* p, const std::vector<PairHost>& all, const double* f, s
   }
 }
 
-// finish rhoofr: scalars from d_red (layout: [2*count kin/dotp][kSumBlocks rho partials])
+// finish rhoofr: scalars from d_red (layout: [kRedPerState*count kin/dotp partials][kSumBlocks rho partials])
 void finish_rho_scalars(cpb_plan* p, const double* f, int first, int count, double* ekin, double* rsum_g,
                         double* rsum_r) {
   double xkin = 0.0, rsum = 0.0;
   for (int i = 0; i < count; ++i) {
     const double fi = f[first + i];
     if (fi != 0.0) {  // kin_energy_utils.mod.F90:66
-      rsum += fi * p->h_red[2 * i + 1];
-      xkin += fi * p->h_red[2 * i];
+      double sk = 0.0, sd = 0.0;
+      for (int c = 0; c < kKinChunks; ++c) {
+        sk += p->h_red[(size_t)kRedPerState * i + 2 * c];
+        sd += p->h_red[(size_t)kRedPerState * i + 2 * c + 1];
+      }
+      rsum += fi * sd;
+      xkin += fi * sk;
     }
   }
   double s = 0.0;
-  for (int i = 0; i < kSumBlocks; ++i) s += p->h_red[2 * count + i];
+  for (int i = 0; i < kSumBlocks; ++i) s += p->h_red[(size_t)kRedPerState * count + i];
   if (ekin) *ekin = xkin * p->tpiba2;
   if (rsum_g) *rsum_g = rsum;
   if (rsum_r) *rsum_r = s * p->omega / ((double)p->nr[0] * p->nr[1] * p->nr[2]);
@@ -524,8 +545,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       throw Error(CPB_ERR_UNSUPPORTED, buf);
     }
     const int n1 = nr[0], n2 = nr[1], n3 = nr[2];
-    const int SL = p->kx->sl, LD = SL;  // XCfg::LDB
-    if ((long)n1 * LD > 65535) throw Error(CPB_ERR_UNSUPPORTED, "n1 too large for 16-bit tile locations");
+    const int SL = p->kx->sl;
 
     // ---- 0-based box positions; the mirror of g is n-g (inyh -> 2*nh-inyh, fftprp :272-277)
     std::vector<int> gx(ngw), gy(ngw), gz(ngw);
@@ -592,69 +612,19 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       p->indzs[i] = (n1 - gx[i]) + 1 + refray[(size_t)(n3 - gz[i]) * n2 + (n2 - gy[i])] * kr[0];
     }
 
-    // ---- mirror-closed ray tiles for the x pass
-    std::vector<int> tile_of(nrays, -1), slot_of(nrays, -1), slot_ray;
-    std::vector<int> ray_y(nrays), ray_z(nrays);
-    for (int zr = 0; zr < nzb; ++zr)
-      for (int y = ylo[zr]; y <= yhi[zr]; ++y) {
-        ray_y[rayoff[zr] + y - ylo[zr]] = y;
-        ray_z[rayoff[zr] + y - ylo[zr]] = zr + zlo;
-      }
-    int ntiles = 0;
-    const int half = SL / 2;
-    for (int zr = 0; zr < nzb; ++zr) {
-      int y = ylo[zr];
-      while (y <= yhi[zr]) {
-        if (tile_of[ray_of(y, zr + zlo)] >= 0) {
-          ++y;
-          continue;
-        }
-        const int t = ntiles++;
-        slot_ray.resize((size_t)ntiles * SL, -1);
-        int ns = 0;
-        int na = 0;
-        while (na < half && y <= yhi[zr]) {
-          const int r = ray_of(y, zr + zlo);
-          if (tile_of[r] < 0) {
-            tile_of[r] = t;
-            slot_of[r] = ns;
-            slot_ray[(size_t)t * SL + ns] = r;
-            ++ns;
-            ++na;
-          }
-          ++y;
-        }
-        for (int s = 0; s < na; ++s) {
-          const int r = slot_ray[(size_t)t * SL + s];
-          const int mr = ray_of(n2 - ray_y[r], n3 - ray_z[r]);
-          if (mr < 0) throw Error(CPB_ERR_INVALID, "internal: ray set is not mirror symmetric");
-          if (tile_of[mr] < 0) {
-            tile_of[mr] = t;
-            slot_of[mr] = ns;
-            slot_ray[(size_t)t * SL + ns] = mr;
-            ++ns;
-          } else if (tile_of[mr] != t) {
-            throw Error(CPB_ERR_INVALID, "internal: mirror ray already owned by another tile");
-          }
-        }
-      }
-    }
-
-    // ---- G entries per tile
-    struct Ent {
-      int tile, ig;
-      uint32_t loc;
-    };
-    std::vector<Ent> ents(ngw);
+    // ---- band-ray storage positions of +G / -G (k_pack / k_unpack): xb * nrp + ray
+    const int nxb = xhi - xlo + 1;
+    const int nrp = (nrays + SL - 1) / SL * SL;
+    if ((double)nxb * nrp > 4.0e9) throw Error(CPB_ERR_UNSUPPORTED, "band-ray storage exceeds 32-bit positions");
+    std::vector<uint32_t> gpos(ngw), gneg(ngw);
     {
       std::vector<unsigned char> occ((size_t)nrays * n1, 0);
       for (int i = 0; i < ngw; ++i) {
         const int rp = ray_of(gy[i], gz[i]);
         const int rm = ray_of(n2 - gy[i], n3 - gz[i]);
-        const int t = tile_of[rp];
-        if (tile_of[rm] != t) throw Error(CPB_ERR_INVALID, "internal: +G and -G rays in different tiles");
-        const uint32_t lp = (uint32_t)(gx[i] * LD + slot_of[rp]);
-        const uint32_t lm = (uint32_t)((n1 - gx[i]) * LD + slot_of[rm]);
+        if (rp < 0 || rm < 0) throw Error(CPB_ERR_INVALID, "internal: ray set is not mirror symmetric");
+        const uint32_t lp = (uint32_t)(gx[i] - xlo) * (uint32_t)nrp + (uint32_t)rp;
+        const uint32_t lm = (uint32_t)(n1 - gx[i] - xlo) * (uint32_t)nrp + (uint32_t)rm;
         if (occ[(size_t)rp * n1 + gx[i]]++) throw Error(CPB_ERR_INVALID, "duplicate plane wave in inyh");
         if (lm != lp) {
           if (occ[(size_t)rm * n1 + (n1 - gx[i])]++)
@@ -662,23 +632,9 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
         } else if (i != 0 || !p->geq0) {
           throw Error(CPB_ERR_INVALID, "self-mirrored plane wave that is not G=0");
         }
-        ents[i].tile = t;
-        ents[i].ig = i;
-        ents[i].loc = lp | (lm << 16);
+        gpos[i] = lp;
+        gneg[i] = lm;
       }
-    }
-    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.tile < b.tile; });
-    std::vector<int> ent_off(ntiles + 1, 0), ent_ig(ngw);
-    std::vector<uint32_t> ent_loc(ngw);
-    for (int i = 0; i < ngw; ++i) {
-      ent_off[ents[i].tile + 1]++;
-      ent_ig[i] = ents[i].ig;
-      ent_loc[i] = ents[i].loc;
-    }
-    int max_tile_ent = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      max_tile_ent = std::max(max_tile_ent, ent_off[t + 1]);
-      ent_off[t + 1] += ent_off[t];
     }
 
     {
@@ -692,9 +648,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       auto fits = [](const AxisKernels* k, int lo, int hi) {
         return lo >= k->r2 * k->klo && hi < k->r2 * k->khi;
       };
-      p->half_x = fits(p->kx, xlo, xhi) && max_tile_ent <= p->kx->x_ept_half * p->kx->x_threads;
-      if (max_tile_ent > p->kx->x_ept_full * p->kx->x_threads)
-        throw Error(CPB_ERR_UNSUPPORTED, "x-pass tile holds more plane waves than the kernel's register budget");
+      p->half_x = fits(p->kx, xlo, xhi);
       p->half_y = fits(p->ky, ymin, ymax);
       p->half_z = fits(p->kz, zlo, zhi);
       if (const char* e = std::getenv("CPB_NO_HALF")) {
@@ -707,8 +661,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->nzb = nzb;
     p->nrays = nrays;
     p->ref_nrays = nref;
-    p->ntiles = ntiles;
-    p->nent = ngw;
+    p->nrp = nrp;
 
     // ---- device side
     rt::set_device(device);
@@ -716,37 +669,39 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->d_ylo = upload(ylo);
     p->d_yhi = upload(yhi);
     p->d_rayoff = upload(rayoff);
-    p->d_slot_ray = upload(slot_ray);
-    p->d_ent_off = upload(ent_off);
-    p->d_ent_ig = upload(ent_ig);
-    p->d_ent_loc = upload(ent_loc);
+    p->d_gpos = upload(gpos);
+    p->d_gneg = upload(gneg);
     p->d_hg = upload(std::vector<double>(hg, hg + ngw));
     p->d_tw1 = upload(make_twiddles(n1));
     p->d_tw2 = upload(make_twiddles(n2));
     p->d_tw3 = upload(make_twiddles(n3));
-    // T1[pair][xt][ray][B]; T2[pair][xtc][y][zr][B] for one chunk of x tiles, sized so that the
-    // chunk of a whole batch stays L2-resident between the y and z passes (126 MB L2 on B200).
+    // T1[pair][xt][ray][B]; T2[pair][xtc][y][zr][B].  By default T2 holds all x tiles of the batch
+    // (one y launch + one z launch per batch).  Measured on B200 (profiles/r01b_sweep_chunk.txt):
+    // splitting the y/z passes into L2-sized chunks of x tiles loses more to small grids and launch
+    // gaps than the L2 residency of T2 saves, so chunking is a tuning hook only (CPB_CHUNK_XT).
     const int Bx = p->kx->b;
     p->nxt = (n1 + Bx - 1) / Bx;
-    {
-      const size_t per_xt = (size_t)p->max_batch * n2 * nzb * Bx * sizeof(cplx);
-      size_t budget = (size_t)48 << 20;
-      if (const char* e = std::getenv("CPB_L2_CHUNK_MB")) budget = (size_t)std::max(1, std::atoi(e)) << 20;
-      p->chunk_xt = (int)std::max<size_t>(1, std::min<size_t>(p->nxt, budget / std::max<size_t>(per_xt, 1)));
-      if (const char* e = std::getenv("CPB_CHUNK_XT")) p->chunk_xt = std::max(1, std::min(p->nxt, std::atoi(e)));
-    }
+    p->chunk_xt = p->nxt;
+    if (const char* e = std::getenv("CPB_CHUNK_XT")) p->chunk_xt = std::max(1, std::min(p->nxt, std::atoi(e)));
     p->t1_pair = (size_t)p->nxt * nrays * Bx;
     if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("CPB_X_PREFETCH")) p->x_prefetch = std::atoi(e);
+    p->x_sub = std::min(p->x_sub, p->max_batch);
+    p->g_pair = (size_t)nxb * nrp;
+    const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
     p->T1 = (cplx*)rt::dmalloc(t1);
     p->T2 = (cplx*)rt::dmalloc(t2);
-    // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite
+    p->G = (cplx*)rt::dmalloc(gb);
+    p->Gf = (cplx*)rt::dmalloc(gb);
+    // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite.
+    // G: positions that hold no plane wave are never written by any kernel and must stay zero.
     rt::dzero(p->T1, t1, 0);
     rt::dzero(p->T2, t2, 0);
+    rt::dzero(p->G, gb, 0);
+    rt::dzero(p->Gf, gb, 0);
     rt::sync(0);
-    p->workspace_bytes = t1 + t2;
+    p->workspace_bytes = t1 + t2 + 2 * gb;
     p->s_main = rt::stream_create();
     p->s_in = rt::stream_create();
     p->s_out = rt::stream_create();
@@ -759,19 +714,18 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     pd.kr2 = kr[1];
     pd.kr3 = kr[2];
     pd.xlo = xlo;
-    pd.xhi = xhi;
+    pd.nxb = nxb;
     pd.zlo = zlo;
     pd.nzb = nzb;
     pd.nrays = nrays;
-    pd.ntiles = ntiles;
+    pd.nrp = nrp;
     pd.nxt = p->nxt;
+    pd.ngw = ngw;
     pd.ylo = p->d_ylo;
     pd.yhi = p->d_yhi;
     pd.rayoff = p->d_rayoff;
-    pd.slot_ray = p->d_slot_ray;
-    pd.ent_off = p->d_ent_off;
-    pd.ent_ig = p->d_ent_ig;
-    pd.ent_loc = p->d_ent_loc;
+    pd.gpos = p->d_gpos;
+    pd.gneg = p->d_gneg;
     pd.hg = p->d_hg;
     pd.tw1 = p->d_tw1;
     pd.tw2 = p->d_tw2;
@@ -870,12 +824,12 @@ int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, cons
     std::vector<PairHost> pairs;
     std::vector<double> ca, cb;
     rho_coefs(p, block_pairs(nstate, my_group, ngroups), f, pairs, ca, cb);
-    ensure_red(p, 2 * nblk + kSumBlocks);
+    ensure_red(p, kRedPerState * nblk + kSumBlocks);
     rt::dzero(rhoe_dev, p->nnr1() * sizeof(double), st);  // rhoofr_utils.mod.F90:198
     launch_kin(p, c0, ld_c0, first, nblk, st);               // :178
     run_rhoofr(p, c0, ld_c0, pairs, ca, cb, rhoe_dev, st, nullptr);
-    launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + 2 * nblk, st);  // :607-619
-    rt::d2h(p->h_red, p->d_red, (size_t)(2 * nblk + kSumBlocks) * sizeof(double), st);
+    launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + kRedPerState * nblk, st);  // :607-619
+    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + kSumBlocks) * sizeof(double), st);
     rt::sync(st);
     resolve_spans(p);
     double rg = 0, rr = 0;

@@ -84,4 +84,54 @@ CPB_D void l2_prefetch(const void* p, unsigned bytes) {
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// Bulk asynchronous copies global -> shared (TMA engine, 1-D: cp.async.bulk, SASS UBLKCP) with
+// mbarrier transaction counting.  One elected thread arms the barrier with the byte count and
+// issues the copy; every consumer thread waits on the barrier's phase parity before it reads the
+// tile with ordinary shared-memory loads.  `bytes` and both addresses are multiples of 16.
+// In the simulator build the copy happens at issue time and the waits are no-ops, which is a legal
+// schedule: the source was written by an earlier kernel, and the destination stage is only
+// re-armed after a block barrier that follows its last read.
+// ---------------------------------------------------------------------------------------------
+#if defined(CPB_EMULATE)
+inline void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(uint64_t*, unsigned) {}
+inline void mbar_wait(uint64_t*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t*) {
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
+}
+#else
+CPB_D unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+CPB_D void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+CPB_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CPB_D void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+CPB_D void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CPB_MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CPB_MBAR_DONE_%=;\n"
+      "bra CPB_MBAR_WAIT_%=;\n"
+      "CPB_MBAR_DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+CPB_D void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif
+
 }  // namespace cpb

@@ -1,22 +1,30 @@
-// Small reduction kernels (included by cpb200.cu only).
+// Mesh-length independent kernels: G-space pack / unpack and the reductions (included by
+// cpb200.cu only).
 #pragma once
-#include "cpb_defs.h"
+#include "kernels.h"
 
 namespace cpb {
 
 // ---------------------------------------------------------------------------------------------
 // G-space reductions of kin_energy (kin_energy_utils.mod.F90:62-110) and dotp
-// (dotp_utils.mod.F90:26-53): one block per state, fixed-order tree reduction (bit-stable).
-// out[2*i] = sum_G hg |c|^2 ; out[2*i+1] = dotp(c,c).   block = 256
+// (dotp_utils.mod.F90:26-53).  grid = (kKinChunks, states): block (c, st) reduces its contiguous
+// slice of the plane waves of one state in a fixed order (bit-stable); the host adds the
+// kKinChunks partials of a state in order.
+// out[(st*kKinChunks + c)*2] = sum_G hg |c|^2 ; out[.. + 1] = dotp(c,c).   block = 256
 // ---------------------------------------------------------------------------------------------
+constexpr int kKinChunks = 8;
+
 CPB_GLOBAL k_kin_energy(const cplx* CPB_RESTRICT c0, long ldc, int first_state, int ngw, int geq0,
                         const double* CPB_RESTRICT hg, double* CPB_RESTRICT out) {
   CPB_DYN_SMEM(double, red);  // 2*256
   const int tid = threadIdx.x;
-  const int st = blockIdx.x;
+  const int st = blockIdx.y;
+  const int per = (ngw + kKinChunks - 1) / kKinChunks;
+  const int g0 = blockIdx.x * per;
+  const int g1 = (g0 + per < ngw) ? g0 + per : ngw;
   const cplx* c = c0 + (size_t)(first_state + st) * ldc;
   double sk = 0.0, sd = 0.0;
-  for (int ig = tid; ig < ngw; ig += 256) {
+  for (int ig = g0 + tid; ig < g1; ig += 256) {
     const cplx a = c[ig];
     const double m = a.x * a.x + a.y * a.y;
     sk += hg[ig] * m;
@@ -37,8 +45,8 @@ CPB_GLOBAL k_kin_energy(const cplx* CPB_RESTRICT c0, long ldc, int first_state, 
     __syncthreads();
   }
   if (tid == 0) {
-    out[2 * st] = red[0];
-    out[2 * st + 1] = red[256];
+    out[((size_t)st * kKinChunks + blockIdx.x) * 2] = red[0];
+    out[((size_t)st * kKinChunks + blockIdx.x) * 2 + 1] = red[256];
   }
 }
 
@@ -58,23 +66,87 @@ CPB_GLOBAL k_sum(const double* CPB_RESTRICT a, size_t n, double* CPB_RESTRICT pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage the plane-wave columns of a group of pairs in L2 with sequential TMA bulk prefetches.
-// The x passes gather/scatter 16-byte coefficients at random positions of these columns
-// (nzhs/indzs order vs |G|^2 order); straight from HBM that access pattern is bound by the DRAM
-// row-activation rate, from L2 it is not.  grid = (ceil(ngw*16 / (256*CHUNK)), ncols), block = 256
+// k_pack: set_psi_2_states_g / set_psi_1_state_g (state_utils.mod.F90:132-189) into the band-ray
+// storage G[pair][xb][ray] (see kernels.h):  G(+G) = c1 + i c2,  G(-G) = conj(c1) + i conj(c2),
+// G = 0 written once (state_utils.mod.F90:187).  Positions that hold no plane wave are never
+// written by any kernel and stay zero from plan creation (the reference zeroes psi per pair,
+// rhoofr_utils.mod.F90:328, vpsi_utils.mod.F90:428).  One thread = one plane wave, looping over
+// the pairs of its group; c0 is read fully coalesced, the 16-byte scatter lands in L2.
+// grid = (ceil(ngw/256), pair groups), block = 256
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned kPrefetchChunk = 2048;  // bytes per thread
+constexpr int kPackUnroll = 4;
 
-CPB_GLOBAL k_l2_prefetch_cols(const cplx* CPB_RESTRICT base, long ldc, const int* CPB_RESTRICT st1,
-                              const int* CPB_RESTRICT st2, int npair, int ngw) {
-  const int col = blockIdx.y;  // 0 .. 2*npair-1
-  const int s = (col < npair) ? st1[col] : st2[col - npair];
-  if (s < 0) return;
-  const size_t bytes = (size_t)ngw * sizeof(cplx);
-  const size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kPrefetchChunk;
-  if (off >= bytes) return;
-  const size_t n = (bytes - off < kPrefetchChunk) ? bytes - off : kPrefetchChunk;
-  l2_prefetch(reinterpret_cast<const char*>(base + (size_t)s * ldc) + off, (unsigned)n);
+CPB_GLOBAL k_pack(const cplx* CPB_RESTRICT c0, long ldc, cplx* CPB_RESTRICT G, PlanDev pd, PairDev pr,
+                  int npair, int ppg) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  const uint32_t lp = pd.gpos[ig], lm = pd.gneg[ig];
+  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
+  for (int q0 = p0; q0 < p1; q0 += kPackUnroll) {
+    cplx a[kPackUnroll], b[kPackUnroll];
+    static_for<0, kPackUnroll>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      if (q0 + j < p1) {
+        const int s1 = pr.st1[q0 + j], s2 = pr.st2[q0 + j];
+        a[j] = c0[(size_t)s1 * ldc + ig];
+        b[j] = (s2 >= 0) ? c0[(size_t)s2 * ldc + ig] : mk(0.0, 0.0);
+      }
+    });
+    static_for<0, kPackUnroll>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      if (q0 + j < p1) {
+        cplx* g = G + (size_t)(q0 + j) * g_pair;
+        g[lp] = mk(a[j].x - b[j].y, a[j].y + b[j].x);                // c1 + i c2
+        if (lm != lp) g[lm] = mk(a[j].x + b[j].y, b[j].x - a[j].y);  // conj(c1) + i conj(c2)
+      }
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_unpack: vpsi_utils.mod.F90:626-673 + add_wfn (:717).  Reads FFT[V psi] at +G and -G from the
+// band-ray storage (already scaled by 1/N in k_x_fwd), separates the two states, adds the
+// kinetic term, scales by -f/2 and updates c2.  ACC: c2 += result (reference semantics);
+// !ACC: c2 = result.  grid = (ceil(ngw/256), pair groups), block = 256
+// ---------------------------------------------------------------------------------------------
+template <bool ACC>
+CPB_GLOBAL k_unpack(const cplx* CPB_RESTRICT G, const cplx* CPB_RESTRICT c0, cplx* CPB_RESTRICT c2, long ldc,
+                    PlanDev pd, PairDev pr, int npair, int ppg) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  const uint32_t lp = pd.gpos[ig], lm = pd.gneg[ig];
+  const double g2 = pd.tpiba2 * pd.hg[ig];
+  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
+  for (int pair = p0; pair < p1; ++pair) {
+    const int s1 = pr.st1[pair], s2 = pr.st2[pair];
+    const double fi = pr.ca[pair], fip1 = pr.cb[pair];
+    const cplx* g = G + (size_t)pair * g_pair;
+    const cplx psin = g[lp];
+    const cplx psii = g[lm];
+    cplx* o1 = c2 + (size_t)s1 * ldc + ig;
+    cplx* o2 = c2 + (size_t)(s2 < 0 ? s1 : s2) * ldc + ig;
+    const cplx a = c0[(size_t)s1 * ldc + ig];
+    const cplx bq = (s2 >= 0) ? c0[(size_t)s2 * ldc + ig] : mk(0.0, 0.0);
+    cplx old1 = mk(0.0, 0.0), old2 = mk(0.0, 0.0);
+    if (ACC) {
+      old1 = *o1;
+      if (s2 >= 0) old2 = *o2;
+    }
+    const cplx fp = cadd(psin, psii);
+    const cplx fm = csub(psin, psii);
+    cplx r1 = mk(-fi * (g2 * a.x + fp.x), -fi * (g2 * a.y + fm.y));
+    if (ACC) r1 = cadd(r1, old1);
+    *o1 = r1;
+    if (s2 >= 0) {
+      cplx r2 = mk(-fip1 * (g2 * bq.x + fp.y), -fip1 * (g2 * bq.y - fm.x));
+      if (ACC) r2 = cadd(r2, old2);
+      *o2 = r2;
+    }
+  }
 }
 
 }  // namespace cpb
