@@ -10,7 +10,7 @@ namespace cpb {
 #define CPB_B 8    // batch columns (consecutive x) per block in the y/z passes: 8*16 B = 128 B rows
 #endif
 #ifndef CPB_SL
-#define CPB_SL 16  // consecutive rays per block in the x pass
+#define CPB_SL 8   // consecutive rays per block in the x pass
 #endif
 
 struct AxisKernels {
@@ -19,7 +19,8 @@ struct AxisKernels {
   int klo, khi;  // band-pruned k range of the first radix pass: index band must lie in [r2*klo, r2*khi)
   // x passes on the band-ray storage G (see kernels.h): `ppg` = pairs per block (pair groups in
   // grid.y), `half` = band-pruned instantiation
-  void (*x_inv)(cudaStream_t, const cplx* G, cplx* T1, const PlanDev&, int npair, int ppg, bool half);
+  void (*x_inv)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
+                int ppg, bool half);
   void (*x_fwd)(cudaStream_t, const cplx* T1, cplx* G, const PlanDev&, int npair, int ppg, bool half);
   // y/z passes work on one chunk of x tiles [xt0, xt0+nxc) (T2 holds that chunk only); `half`
   // selects the band-pruned instantiation (KRange), `ppg` = pairs per block (pair groups in grid.z)

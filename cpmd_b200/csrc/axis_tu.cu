@@ -41,23 +41,26 @@ void allow_smem(K kern, size_t bytes) {
 constexpr size_t kSmemYZ = (size_t)N * B * sizeof(cplx);
 
 template <bool HALF>
-void x_inv_t(cudaStream_t st, const cplx* G, cplx* T1, const PlanDev& pd, int npair, int ppg) {
+void x_inv_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+             int ppg) {
   using C = XCfg<R1, R2, SL>;
   auto k = k_x_inv<R1, R2, SL, B, HALF>;
-  allow_smem(k, C::SMEM);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM, st, G, T1, pd, npair, ppg);
+  const size_t smem = C::smem_inv(KRange<R1, HALF>::cnt);
+  allow_smem(k, smem);
+  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg);
 }
-void x_inv(cudaStream_t st, const cplx* G, cplx* T1, const PlanDev& pd, int npair, int ppg, bool half) {
-  if (half) x_inv_t<true>(st, G, T1, pd, npair, ppg);
-  else x_inv_t<false>(st, G, T1, pd, npair, ppg);
+void x_inv(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+           int ppg, bool half) {
+  if (half) x_inv_t<true>(st, c0, ldc, T1, pd, pr, npair, ppg);
+  else x_inv_t<false>(st, c0, ldc, T1, pd, pr, npair, ppg);
 }
 
 template <bool HALF>
 void x_fwd_t(cudaStream_t st, const cplx* T1, cplx* G, const PlanDev& pd, int npair, int ppg) {
   using C = XCfg<R1, R2, SL>;
   auto k = k_x_fwd<R1, R2, SL, B, HALF>;
-  allow_smem(k, C::SMEM);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM, st, T1, G, pd, npair, ppg);
+  allow_smem(k, C::SMEM_FWD);
+  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_FWD, st, T1, G, pd, npair, ppg);
 }
 void x_fwd(cudaStream_t st, const cplx* T1, cplx* G, const PlanDev& pd, int npair, int ppg, bool half) {
   if (half) x_fwd_t<true>(st, T1, G, pd, npair, ppg);
@@ -68,9 +71,10 @@ constexpr size_t kSmemYZ2 = 2 * kSmemYZ;  // double-buffered exchange
 
 template <bool HALF>
 void y_inv_t(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npair, int xt0, int nxc, int ppg) {
-  auto k = k_y_inv<R1, R2, B, HALF>;
-  allow_smem(k, kSmemYZ2);
-  CPB_LAUNCH(k, dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg), dim3(B * RM), kSmemYZ2, st, T1, T2, pd, xt0, npair, ppg);
+  auto k = k_y_inv<R1, R2, B, HALF, CPB_YINV_XB>;
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nyb * B, CPB_YINV_XB);
+  allow_smem(k, smem);
+  CPB_LAUNCH(k, dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T1, T2, pd, xt0, npair, ppg);
 }
 void y_inv(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
            bool half) {
@@ -93,8 +97,8 @@ void y_fwd(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npa
 template <bool HALF>
 void z_rho_t(cudaStream_t st, const cplx* T2, double* rho, const PlanDev& pd, const PairDev& pr, int npair,
              int xt0, int nxc) {
-  auto k = k_z_rho<R1, R2, B, HALF>;
-  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B);
+  auto k = k_z_rho<R1, R2, B, HALF, CPB_ZRHO_XB>;
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B, CPB_ZRHO_XB);
   allow_smem(k, smem);
   CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), smem, st, T2, rho, pd, pr, npair, xt0);
 }
@@ -108,8 +112,9 @@ template <bool HALF>
 void z_vpsi_t(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
               int ppg) {
   auto k = k_z_vpsi<R1, R2, B, HALF>;
-  allow_smem(k, kSmemYZ2);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2, (npair + ppg - 1) / ppg), dim3(B * RM), kSmemYZ2, st, T2, vpot, pd, xt0, npair, ppg);
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B);
+  allow_smem(k, smem);
+  CPB_LAUNCH(k, dim3(nxc, pd.n2, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T2, vpot, pd, xt0, npair, ppg);
 }
 void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
             int ppg, bool half) {

@@ -74,7 +74,7 @@ struct cpb_plan {
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
-  int x_sub = 4;          // pairs per x-pass sub-batch (its band-ray storage G stays in L2)
+  int x_sub = 4;          // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
@@ -85,12 +85,11 @@ struct cpb_plan {
   // device data
   PlanDev pd;
   int *d_ylo = nullptr, *d_yhi = nullptr, *d_rayoff = nullptr;
-  uint32_t *d_gpos = nullptr, *d_gneg = nullptr;
+  uint32_t *d_gpos = nullptr, *d_gneg = nullptr, *d_gtab = nullptr;
   double* d_hg = nullptr;
   cplx *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw3 = nullptr;
   cplx *T1 = nullptr, *T2 = nullptr;
-  cplx *G = nullptr;   // band-ray storage, inverse side: non-plane-wave positions stay zero forever
-  cplx *Gf = nullptr;  // band-ray storage, forward side (fully overwritten by k_x_fwd)
+  cplx *G = nullptr;   // band-ray storage of one x_sub sub-batch (written by k_x_fwd, read by k_unpack)
   size_t workspace_bytes = 0;
   // per-call pair descriptors
   int pair_cap = 0;
@@ -138,8 +137,8 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_rayoff);
   rt::dfree(p->d_gpos);
   rt::dfree(p->d_gneg);
+  rt::dfree(p->d_gtab);
   rt::dfree(p->G);
-  rt::dfree(p->Gf);
   rt::dfree(p->d_hg);
   rt::dfree(p->d_tw1);
   rt::dfree(p->d_tw2);
@@ -306,32 +305,40 @@ int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group) {
 
 
 // pair groups for the elementwise G-space kernels: enough blocks to fill the machine a few times
-int ew_ppg(const cpb_plan* p, int npair) {
+int ew_ppg(const cpb_plan* p, int npair, int waves) {
   const int bx = (p->ngw + 255) / 256;
-  int groups = (8 * p->n_sm + bx - 1) / bx;
+  int groups = (waves * p->n_sm + bx - 1) / bx;
   groups = std::max(1, std::min(groups, npair));
   return (npair + groups - 1) / groups;
 }
 
-// x passes in sub-batches of x_sub pairs: k_pack fills the sub-batch's band-ray storage G (it stays
-// in L2), the x FFT streams it into T1; the forward direction is the mirror with k_unpack last.
-void run_x_inv(cpb_plan* p, const cplx* c0, long ldc, const PairDev& prb, int nb, cudaStream_t st) {
-  for (int o = 0; o < nb; o += p->x_sub) {
-    const int ns = std::min(p->x_sub, nb - o);
-    PairDev prs = offset_pairs(prb, o);
-    {
-      Timed t(p, st, CPB_K_PACK);
-      const int ppg = ew_ppg(p, ns);
-      auto k = k_pack;
-      CPB_LAUNCH(k, dim3((p->ngw + 255) / 256, (ns + ppg - 1) / ppg), dim3(256), 0, st, c0, ldc, p->G, p->pd, prs,
-                 ns, ppg);
+// pairs per block of the inverse x pass: long enough loops to amortise the block prologue while the
+// grid still fills the machine several times (the last, partial wave costs 1/waves of the time)
+int x_inv_ppg(const cpb_plan* p, int npair) {
+  const int tiles = p->nrp / p->kx->sl;
+  const int slots = p->n_sm * 4;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ppg = 1; ppg <= std::min(npair, 8); ++ppg) {
+    const long blocks = (long)tiles * ((npair + ppg - 1) / ppg);
+    const long waves = (blocks + slots - 1) / slots;
+    const double cost = (double)waves * (ppg + 0.5);  // 0.5 pair-times of prologue per block
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = ppg;
     }
-    Timed t(p, st, CPB_K_X_INV);
-    p->kx->x_inv(st, p->G, p->T1 + (size_t)o * p->t1_pair, p->pd, ns, pairs_per_group(p, ns, p->nrp / p->kx->sl),
-                 p->half_x);
   }
+  return best;
 }
 
+// x pass, inverse: one launch per batch; the kernel gathers the coefficients from c0 itself
+void run_x_inv(cpb_plan* p, const cplx* c0, long ldc, const PairDev& prb, int nb, cudaStream_t st) {
+  Timed t(p, st, CPB_K_X_INV);
+  p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb, x_inv_ppg(p, nb), p->half_x);
+}
+
+// x pass, forward, in sub-batches of x_sub pairs: k_x_fwd writes the sub-batch's band-ray storage
+// (it stays in L2), k_unpack gathers +G / -G from it and updates c2.
 void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb, bool accumulate,
                cudaStream_t st) {
   for (int o = 0; o < nb; o += p->x_sub) {
@@ -339,18 +346,18 @@ void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& p
     PairDev prs = offset_pairs(prb, o);
     {
       Timed t(p, st, CPB_K_X_FWD);
-      p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, p->Gf, p->pd, ns,
+      p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, p->G, p->pd, ns,
                    pairs_per_group(p, ns, p->nrp / p->kx->sl), p->half_x);
     }
     Timed t(p, st, CPB_K_UNPACK);
-    const int ppg = ew_ppg(p, ns);
+    const int ppg = ew_ppg(p, ns, 8);
     const dim3 grid((p->ngw + 255) / 256, (ns + ppg - 1) / ppg);
     if (accumulate) {
       auto k = k_unpack<true>;
-      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->Gf, c0, c2, ldc, p->pd, prs, ns, ppg);
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->G, c0, c2, ldc, p->pd, prs, ns, ppg);
     } else {
       auto k = k_unpack<false>;
-      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->Gf, c0, c2, ldc, p->pd, prs, ns, ppg);
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->G, c0, c2, ldc, p->pd, prs, ns, ppg);
     }
   }
 }
@@ -600,6 +607,8 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       rayoff[z - zlo] = nrays;
       nrays += hi - lo + 1;
     }
+    int nyb = 1;
+    for (int zr = 0; zr < nzb; ++zr) nyb = std::max(nyb, yhi[zr] - ylo[zr] + 1);
     auto ray_of = [&](int y, int z) -> int {
       const int zr = z - zlo;
       if (zr < 0 || zr >= nzb || y < ylo[zr] || y > yhi[zr]) return -1;
@@ -612,11 +621,12 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       p->indzs[i] = (n1 - gx[i]) + 1 + refray[(size_t)(n3 - gz[i]) * n2 + (n2 - gy[i])] * kr[0];
     }
 
-    // ---- band-ray storage positions of +G / -G (k_pack / k_unpack): xb * nrp + ray
+    // ---- band-ray storage positions of +G / -G (k_x_inv's gtab, k_unpack's gpos/gneg): xb * nrp + ray
     const int nxb = xhi - xlo + 1;
     const int nrp = (nrays + SL - 1) / SL * SL;
     if ((double)nxb * nrp > 4.0e9) throw Error(CPB_ERR_UNSUPPORTED, "band-ray storage exceeds 32-bit positions");
-    std::vector<uint32_t> gpos(ngw), gneg(ngw);
+    std::vector<uint32_t> gpos(ngw), gneg(ngw), gtab((size_t)nxb * nrp, kNoPW);
+    if ((unsigned)ngw >= kNegPW) throw Error(CPB_ERR_UNSUPPORTED, "ngw too large");
     {
       std::vector<unsigned char> occ((size_t)nrays * n1, 0);
       for (int i = 0; i < ngw; ++i) {
@@ -634,6 +644,8 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
         }
         gpos[i] = lp;
         gneg[i] = lm;
+        if (lm != lp) gtab[lm] = (uint32_t)i | kNegPW;
+        gtab[lp] = (uint32_t)i;  // G = 0: the +G form is the one stored (state_utils.mod.F90:187)
       }
     }
 
@@ -671,6 +683,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->d_rayoff = upload(rayoff);
     p->d_gpos = upload(gpos);
     p->d_gneg = upload(gneg);
+    p->d_gtab = upload(gtab);
     p->d_hg = upload(std::vector<double>(hg, hg + ngw));
     p->d_tw1 = upload(make_twiddles(n1));
     p->d_tw2 = upload(make_twiddles(n2));
@@ -693,15 +706,12 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->T1 = (cplx*)rt::dmalloc(t1);
     p->T2 = (cplx*)rt::dmalloc(t2);
     p->G = (cplx*)rt::dmalloc(gb);
-    p->Gf = (cplx*)rt::dmalloc(gb);
     // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite.
-    // G: positions that hold no plane wave are never written by any kernel and must stay zero.
     rt::dzero(p->T1, t1, 0);
     rt::dzero(p->T2, t2, 0);
     rt::dzero(p->G, gb, 0);
-    rt::dzero(p->Gf, gb, 0);
     rt::sync(0);
-    p->workspace_bytes = t1 + t2 + 2 * gb;
+    p->workspace_bytes = t1 + t2 + gb;
     p->s_main = rt::stream_create();
     p->s_in = rt::stream_create();
     p->s_out = rt::stream_create();
@@ -719,11 +729,13 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     pd.nzb = nzb;
     pd.nrays = nrays;
     pd.nrp = nrp;
+    pd.nyb = nyb;
     pd.nxt = p->nxt;
     pd.ngw = ngw;
     pd.ylo = p->d_ylo;
     pd.yhi = p->d_yhi;
     pd.rayoff = p->d_rayoff;
+    pd.gtab = p->d_gtab;
     pd.gpos = p->d_gpos;
     pd.gneg = p->d_gneg;
     pd.hg = p->d_hg;

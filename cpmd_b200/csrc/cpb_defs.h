@@ -134,4 +134,25 @@ CPB_D void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// 16-byte asynchronous copies global -> shared (cp.async, SASS LDGSTS): the gather of plane-wave
+// coefficients lands in shared memory without holding registers while in flight.  Groups are
+// per thread; in the simulator build the copy happens at issue time.
+// ---------------------------------------------------------------------------------------------
+#if defined(CPB_EMULATE)
+inline void cp_async16(void* dst, const void* src) {
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  for (int i = 0; i < 16; ++i) d[i] = s[i];
+}
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#else
+CPB_D void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+CPB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+CPB_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
 }  // namespace cpb

@@ -2,8 +2,8 @@
 // axis_tu.cu).  See DESIGN.md for the data layout and the byte model.
 //
 // Pipeline per batch of packed state pairs (two real states per complex transform, Gamma point):
-//   rhoofr:  k_pack -> k_x_inv  ->  k_y_inv  ->  k_z_rho
-//   vpsi:    k_pack -> k_x_inv  ->  k_y_inv  ->  k_z_vpsi (z-inverse * V(r) * z-forward, fused)
+//   rhoofr:  k_x_inv (gather + pack + x)  ->  k_y_inv  ->  k_z_rho
+//   vpsi:    k_x_inv  ->  k_y_inv  ->  k_z_vpsi (z-inverse * V(r) * z-forward, fused)
 //                     ->  k_y_fwd  ->  k_x_fwd -> k_unpack (unpack + kinetic + scale + c2 update)
 //
 // Replaces (not ports) the reference's per-pair sequence set_psi_2_states_g -> invfftn ->
@@ -33,12 +33,14 @@ struct PlanDev {
   int xlo, nxb;       // 0-based first x of the band that holds G-sphere coefficients, band width
   int zlo, nzb;       // 0-based first z plane of the band, number of planes (kr3min..kr3max)
   int nrays;          // internal ray count (>= msrays; dense in y inside every plane)
+  int nyb;            // largest number of rays in one z plane (y band width)
   int nrp;            // row pitch of the band-ray storage (nrays rounded up to the x-pass tile)
   int nxt;            // x tiles of B columns: ceil(n1 / B)
   int ngw;
   const int* ylo;     // [nzb] first y with a ray in plane zr (0-based)
   const int* yhi;     // [nzb] last y (ylo > yhi: plane has no ray)
   const int* rayoff;  // [nzb] ray index of (ylo, zr)
+  const uint32_t* gtab;      // [nxb*nrp] plane wave stored at a band-ray position (kNoPW / kNegPW flags)
   const uint32_t* gpos;      // [ngw] band-ray storage position of +G: xb*nrp + ray  (nzhs)
   const uint32_t* gneg;      // [ngw] same for -G                                   (indzs)
   const double* hg;          // [ngw]
@@ -89,18 +91,50 @@ struct YZBlocks {
 template <int RA, int RB, bool INV, int LO, int HI, bool TWS = false, class ST>
 CPB_D void pass_a_st(cplx (&v)[RA], int a, const cplx* CPB_RESTRICT tw, ST&& st) {
   dft_in<RA, INV, LO, HI>(v);
-  static_for<0, RA>([&](auto pp) {
-    constexpr int p = decltype(pp)::value;
-    cplx o = v[p];
-    if constexpr (p != 0) {
-      cplx t;
-      if constexpr (TWS) t = tw[a * p];
-      else t = __ldg(&tw[a * p]);
-      if constexpr (!INV) t.y = -t.y;
-      o = cmul(o, t);
-    }
-    st(p, o);
-  });
+  if constexpr (!TWS) {
+    // global twiddle table through the read-only path: the compiler is free to hoist the loads
+    static_for<0, RA>([&](auto pp) {
+      constexpr int p = decltype(pp)::value;
+      cplx o = v[p];
+      if constexpr (p != 0) {
+        cplx t = __ldg(&tw[a * p]);
+        if constexpr (!INV) t.y = -t.y;
+        o = cmul(o, t);
+      }
+      st(p, o);
+    });
+  } else {
+    // Shared-memory twiddle table: the loads are written in chunks of kTwChunk *before* the stores
+    // of the previous chunk, because the compiler may not hoist a shared-memory load above a
+    // shared-memory store (possible alias) and one load -> multiply -> store chain per output
+    // would expose the load latency RA-1 times.
+    constexpr int kTwChunk = 8;
+    auto load = [&](auto cc, cplx (&t)[kTwChunk]) {
+      constexpr int c0 = decltype(cc)::value;
+      static_for<0, kTwChunk>([&](auto jj) {
+        constexpr int p = c0 + decltype(jj)::value;
+        if constexpr (p < RA) {
+          t[p - c0] = tw[a * p];
+          if constexpr (!INV) t[p - c0].y = -t[p - c0].y;
+        }
+      });
+    };
+    cplx t[kTwChunk];
+    load(IC<1>{}, t);
+    st(0, v[0]);
+    static_for<0, (RA - 1 + kTwChunk - 1) / kTwChunk>([&](auto cc) {
+      constexpr int c0 = 1 + decltype(cc)::value * kTwChunk;
+      static_for<0, kTwChunk>([&](auto jj) {
+        constexpr int p = c0 + decltype(jj)::value;
+        if constexpr (p < RA) v[p] = cmul(v[p], t[p - c0]);
+      });
+      if constexpr (c0 + kTwChunk < RA) load(IC<c0 + kTwChunk>{}, t);
+      static_for<0, kTwChunk>([&](auto jj) {
+        constexpr int p = c0 + decltype(jj)::value;
+        if constexpr (p < RA) st(p, v[p]);
+      });
+    });
+  }
 }
 
 template <int RA, int RB, bool INV, int LO, int HI, bool TWS = false>
@@ -124,19 +158,19 @@ CPB_D void pass_b(cplx (&u)[RB], int p, const cplx* Sb, int LD) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// x passes.  They work on the *band-ray storage* G[pair][xb][ray] (xb = x - xlo over the x band
-// that holds coefficients, ray = internal ray index, row pitch nrp): the reference's compressed
-// ray storage psi(kr1s, msrays) (fftprp_utils.mod.F90:269-285) restricted to the band and stored
-// ray-minor, so that a tile of SL consecutive rays is one contiguous 16*SL-byte row per x.
-// k_pack (misc_kernels.h) fills it from c0, k_unpack reads it back; between them the x FFT kernels
-// below are pure streaming transforms like the y kernels.  The sub-batch's G stays in L2.
+// x passes.  Positions along a ray are addressed like the reference's compressed ray storage
+// psi(kr1s, msrays) (fftprp_utils.mod.F90:269-285) restricted to the x band that holds
+// coefficients and stored ray-minor: pos = xb * nrp + ray (xb = x - xlo, ray = internal ray index,
+// row pitch nrp).  Three plan tables use it: gtab[pos] = plane wave stored at that position
+// (inverse direction: the x kernel gathers c0 itself), gpos/gneg[ig] = positions of +G / -G
+// (forward direction: k_x_fwd writes the band-ray storage G, k_unpack reads it).
 //
 // One block = SL consecutive rays, loops over a group of packed pairs.  Two thread roles:
-//   "slot-major" (slot = tid % SL, row = tid / SL): lanes run along rays -> G rows are coalesced;
+//   "slot-major" (slot = tid % SL, row = tid / SL): lanes run along rays;
 //   "x-major"    (row = tid % R1, slot = tid / R1): lanes run along x -> T1 is touched in
 //                128-byte rows (consecutive lanes = consecutive x of one ray).
 // The exchange buffer SX between the two radix passes is laid out so that both roles access it
-// conflict free (odd row pitch); it is double buffered: one block barrier per transform.
+// conflict free (odd row pitch).
 // grid = (ray tiles, pair groups), block = SL * max(R1,R2)
 // ---------------------------------------------------------------------------------------------
 template <int R1, int R2, int SL>
@@ -146,19 +180,39 @@ struct XCfg {
   static constexpr int NT = SL * RM;
   static constexpr int P1 = R1 | 1;  // odd pitch of SX rows
   static constexpr int SX_ELEMS = R2 * SL * P1;
-  static constexpr size_t SMEM = (size_t)(2 * SX_ELEMS) * sizeof(cplx);
-  static constexpr int MINB = (NT <= 128) ? 3 : 2;
+  static constexpr int MINB = (NT <= 128) ? ((RM <= 16) ? 4 : 3) : 2;  // inverse kernel
+  static constexpr int MINB_FWD = (NT <= 128) ? 3 : 2;
+  // forward kernel: double-buffered exchange
+  static constexpr size_t SMEM_FWD = (size_t)(2 * SX_ELEMS) * sizeof(cplx);
+  // inverse kernel: one exchange buffer + twiddles + the gather stage [2 states][kcnt][R2*SL threads]
+  static constexpr int NA = R2 * SL;  // threads with a slot-major role in the first pass
+  static constexpr size_t smem_inv(int kcnt) { return (size_t)(SX_ELEMS + N + 2 * kcnt * NA) * sizeof(cplx); }
 };
 
-// x pass, inverse: FFT along x of the band-ray storage (fftnew's first mltfft,
-// fftmain_utils.mod.F90:93-94; zero outside the band), output x-tiled T1.
+constexpr uint32_t kNoPW = 0xffffffffu;  // gtab: position holds no plane wave
+constexpr uint32_t kNegPW = 0x80000000u; // gtab: position holds the -G partner of plane wave (value & ~kNegPW)
+
+// x pass, inverse: gather of the pair's coefficients + pack + FFT along x.  Fuses zeroing(psi) +
+// set_psi_2_states_g / set_psi_1_state_g (state_utils.mod.F90:132-189:  psi(+G) = c1 + i c2,
+// psi(-G) = conj(c1) + i conj(c2), G = 0 stored once) with the x mltfft of fftnew
+// (fftmain_utils.mod.F90:93-94).  Every slot-major thread owns the band positions
+// x = rA + R2*k of its ray: it issues 16-byte cp.async gathers of c1[ig], c2[ig] for them into its
+// private slots of the shared-memory stage one pair ahead, and combines them when it starts the
+// pair - no other thread touches those slots, so the gather needs no block barrier, holds no
+// registers while in flight and the coefficients come straight from c0 (no packed copy in
+// memory).  Positions without a plane wave are zeroed once.
 template <int R1, int R2, int SL, int B, bool HALF>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
-    k_x_inv(const cplx* CPB_RESTRICT G, cplx* CPB_RESTRICT T1, PlanDev pd, int npair, int ppg) {
+    k_x_inv(const cplx* CPB_RESTRICT c0, long ldc, cplx* CPB_RESTRICT T1, PlanDev pd, PairDev pr, int npair,
+            int ppg) {
   using C = XCfg<R1, R2, SL>;
   using KR = KRange<R1, HALF>;
-  constexpr int P1 = C::P1;
+  constexpr int N = C::N, NT = C::NT, P1 = C::P1;
   CPB_DYN_SMEM(cplx, S);
+  cplx* SX = S;
+  cplx* TW = S + C::SX_ELEMS;
+  cplx* ST = TW + N;  // [state][k][tid < NA]
+  constexpr int NA = C::NA, KC = KR::cnt;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
@@ -166,34 +220,57 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
   const int pB = tid % R1, slotB = tid / R1;  // x-major role (valid if slotB < SL)
   const int rayA = blockIdx.x * SL + slotA;
   const int rayB = blockIdx.x * SL + slotB;
-  const bool okA = rA < R2 && rayA < pd.nrays;
   const bool okB = slotB < SL && rayB < pd.nrays;
-  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
-  const cplx* src = G + rayA;
-  cplx nv[KR::cnt];
-  auto fetch = [&](int pair) {
-    const cplx* s = src + (size_t)pair * g_pair;
+  for (int i = tid; i < N; i += NT) TW[i] = pd.tw1[i];
+  // my band positions -> plane-wave index (bit 31: -G partner) or kNoPW
+  uint32_t tab[KR::cnt];
+  static_for<0, KR::cnt>([&](auto kk) {
+    constexpr int j = decltype(kk)::value;
+    const int xb = rA + R2 * (KR::lo + j) - pd.xlo;
+    tab[j] = (rA < R2 && xb >= 0 && xb < pd.nxb) ? __ldg(&pd.gtab[(size_t)xb * pd.nrp + rayA]) : kNoPW;
+    if (rA < R2 && tab[j] == kNoPW) {
+      ST[(0 * KC + j) * NA + tid] = mk(0.0, 0.0);
+      ST[(1 * KC + j) * NA + tid] = mk(0.0, 0.0);
+    }
+  });
+  auto gather = [&](int pair) {
+    const int s1 = __ldg(&pr.st1[pair]), s2 = __ldg(&pr.st2[pair]);
+    const cplx* c1p = c0 + (size_t)s1 * ldc;
+    const cplx* c2p = c0 + (size_t)(s2 < 0 ? s1 : s2) * ldc;
     static_for<0, KR::cnt>([&](auto kk) {
-      constexpr int k = KR::lo + decltype(kk)::value;
-      const int xb = rA + R2 * k - pd.xlo;
-      nv[decltype(kk)::value] = (okA && xb >= 0 && xb < pd.nxb) ? s[(size_t)xb * pd.nrp] : mk(0.0, 0.0);
+      constexpr int j = decltype(kk)::value;
+      if (tab[j] != kNoPW) {
+        const uint32_t ig = tab[j] & ~kNegPW;
+        cp_async16(&ST[(0 * KC + j) * NA + tid], c1p + ig);
+        if (s2 >= 0) cp_async16(&ST[(1 * KC + j) * NA + tid], c2p + ig);
+        else ST[(1 * KC + j) * NA + tid] = mk(0.0, 0.0);  // single-state path: c2 = 0
+      }
     });
+    cp_async_commit();
   };
-  if (p0 < p1) fetch(p0);
-  int buf = 0;
+  if (rA < R2 && p0 < p1) gather(p0);
+  __syncthreads();  // twiddles visible
   for (int pair = p0; pair < p1; ++pair) {
-    cplx* SX = S + buf * C::SX_ELEMS;
     if (rA < R2) {
+      cp_async_wait_all();
       cplx v[R1];
       static_for<0, R1>([&](auto kk) {
         constexpr int k = decltype(kk)::value;
-        if constexpr (k >= KR::lo && k < KR::hi) v[k] = nv[k - KR::lo];
-        else v[k] = mk(0.0, 0.0);
+        if constexpr (k >= KR::lo && k < KR::hi) {
+          constexpr int j = k - KR::lo;
+          const cplx a = ST[(0 * KC + j) * NA + tid];
+          const cplx bq = ST[(1 * KC + j) * NA + tid];
+          const double sg = (tab[j] & kNegPW) ? -1.0 : 1.0;
+          // +G: c1 + i c2 = (a.x - b.y, a.y + b.x);  -G: conj(c1) + i conj(c2) = (a.x + b.y, b.x - a.y)
+          v[k] = mk(a.x - sg * bq.y, sg * a.y + bq.x);
+        } else {
+          v[k] = mk(0.0, 0.0);
+        }
       });
+      if (pair + 1 < p1) gather(pair + 1);  // my slots are free again: next pair's gather
       cplx* dst = SX + (rA * SL + slotA) * P1;
-      pass_a_st<R1, R2, true, KR::lo, KR::hi>(v, rA, pd.tw1, [&](int p, cplx o) { dst[p] = o; });
-      if (pair + 1 < p1) fetch(pair + 1);
+      pass_a_st<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, [&](int p, cplx o) { dst[p] = o; });
     }
     __syncthreads();
     if (slotB < SL) {
@@ -212,7 +289,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
         });
       }
     }
-    buf ^= 1;
+    __syncthreads();  // SX is single buffered
   }
 }
 
@@ -220,7 +297,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
 // last mltfft, fftmain_utils.mod.F90:134-136); only the band rows are stored, into the band-ray
 // storage that k_unpack reads.
 template <int R1, int R2, int SL, int B, bool HALF>
-CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
+CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD))
     k_x_fwd(const cplx* CPB_RESTRICT T1, cplx* CPB_RESTRICT G, PlanDev pd, int npair, int ppg) {
   using C = XCfg<R1, R2, SL>;
   using KR = KRange<R1, HALF>;
@@ -293,16 +370,61 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
 // is loaded (inverse) or stored (forward) and the first radix pass skips the zero terms (dft_in).
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
+// Staged variants of the y/z kernels ("bulk" kernels).  Where a block's input tile of one pair is
+// one contiguous run of memory (the band of a column set in T2, the rays of a plane in T1) it is
+// brought into a ring of KStages shared-memory stages by the TMA engine (bulk_g2s, one instruction
+// per tile issued by one thread) instead of per-thread register prefetches: the prefetch distance
+// is KStages pairs, no registers are held by in-flight loads and no per-element address arithmetic
+// is executed.  The twiddle table lives in shared memory too, so nothing inside the pair loop
+// waits on a global load.  Role rotation: the first radix pass only needs R2 of the max(R1,R2)
+// role rows of a block; which warp idles rotates with the pair index so that the four SM
+// sub-partitions carry the same FP64 load.
+// Shared memory: [XB exchange buffers N*B][twiddles N][KStages tiles][KStages mbarriers].
+// XB = 2: one block barrier per transform; XB = 1: two barriers, but the smaller footprint (and a
+// 128-register budget) lets a fourth block share the SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages = 2;
+#ifndef CPB_ZRHO_XB
+#define CPB_ZRHO_XB 2
+#endif
+#ifndef CPB_YINV_XB
+#define CPB_YINV_XB 2
+#endif
+// resident blocks per SM the staged kernels with XB exchange buffers are compiled for
+template <int R1, int R2, int XB>
+struct YZBlocksX {
+  static constexpr int v = YZBlocks<R1, R2>::v + ((XB == 1 && YZBlocks<R1, R2>::v == 3) ? 1 : 0);
+};
+
+template <int R1, int R2, int B>
+struct YZCfg {
+  static constexpr int N = R1 * R2;
+  static constexpr int RM = MaxOf<R1, R2>::v;
+  static constexpr int NT = B * RM;
+  static constexpr int RPW = 32 / B;  // role rows per warp
+  static constexpr bool ROT = (NT % 32 == 0) && (RM % RPW == 0) && (R2 < RM);
+  // bytes of dynamic shared memory for tiles of `tile_elems` complex numbers, `xb` exchange buffers
+  static constexpr size_t smem(int tile_elems, int xb = 2) {
+    return ((size_t)xb * N * B + N + (size_t)kStages * tile_elems) * sizeof(cplx) + kStages * sizeof(uint64_t);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // y pass, inverse.  Block = (x tile of the chunk, z plane of the band, group of pairs).  Reads the
 // rays of the plane (zero outside [ylo,yhi]: unpack_x2y's zero fill, fftutil_utils.mod.F90:413-457),
 // writes all n2 rows of the chunk's T2.  grid = (x tiles of the chunk, nzb, pair groups)
 // ---------------------------------------------------------------------------------------------
-template <int R1, int R2, int B, bool HALF>
-CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
+template <int R1, int R2, int B, bool HALF, int XB>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
     k_y_inv(const cplx* CPB_RESTRICT T1, cplx* CPB_RESTRICT T2, PlanDev pd, int xt0, int npair, int ppg) {
-  constexpr int N = R1 * R2;
+  using C = YZCfg<R1, R2, B>;
+  constexpr int N = C::N, RM = C::RM, NT = C::NT;
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
+  cplx* TW = S + XB * N * B;
+  cplx* ST = TW + N;
+  const int tile_elems = pd.nyb * B;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ST + (size_t)kStages * tile_elems);
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
   const int xtc = blockIdx.x, nxc = gridDim.x;
@@ -310,34 +432,49 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   const int p0 = blockIdx.z * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
   const int ylo = pd.ylo[zr], yhi = pd.yhi[zr];
+  const int ny = yhi - ylo + 1;  // rays of this plane (<= 0: none), one contiguous run of T1
+  const unsigned tile_bytes = (unsigned)(ny > 0 ? ny : 0) * B * (unsigned)sizeof(cplx);
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
   const size_t t2_pair = (size_t)nxc * N * pd.nzb * B;
-  const cplx* src = T1 + ((size_t)(xt0 + xtc) * pd.nrays + pd.rayoff[zr]) * B + b;
+  const cplx* src = T1 + ((size_t)(xt0 + xtc) * pd.nrays + pd.rayoff[zr]) * B;
   cplx* dst = T2 + ((size_t)xtc * N * pd.nzb + zr) * B + b;
-  cplx nv[KR::cnt];
-  auto fetch = [&](int pair) {
-    const cplx* s = src + (size_t)pair * t1_pair;
-    static_for<0, KR::cnt>([&](auto kk) {
-      constexpr int k = KR::lo + decltype(kk)::value;
-      const int y = r + R2 * k;
-      nv[decltype(kk)::value] = (y >= ylo && y <= yhi) ? s[(y - ylo) * B] : mk(0.0, 0.0);
-    });
-  };
-  if (r < R2 && p0 < p1) fetch(p0);
-  int buf = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < N; i += NT) TW[i] = pd.tw2[i];
+  __syncthreads();
+  if (tid == 0 && ny > 0) {
+    for (int s = 0; s < kStages && p0 + s < p1; ++s) {
+      mbar_expect_tx(&bar[s], tile_bytes);
+      bulk_g2s(ST + (size_t)s * tile_elems, src + (size_t)(p0 + s) * t1_pair, tile_bytes, &bar[s]);
+    }
+  }
+  int rA = r;  // role in the first radix pass (rotates by one warp per pair)
   for (int pair = p0; pair < p1; ++pair) {
-    cplx* Sb = S + buf * (N * B) + b;
-    if (r < R2) {
+    const int it = pair - p0;
+    const int st = it % kStages;
+    cplx* Sb = S + (XB == 2 ? (it & 1) : 0) * (N * B) + b;
+    if (rA < R2) {
+      if (ny > 0) mbar_wait(&bar[st], (unsigned)((it / kStages) & 1));
+      const cplx* in = ST + (size_t)st * tile_elems + b;
       cplx v[R1];
       static_for<0, R1>([&](auto kk) {
         constexpr int k = decltype(kk)::value;
-        if constexpr (k >= KR::lo && k < KR::hi) v[k] = nv[k - KR::lo];
-        else v[k] = mk(0.0, 0.0);
+        if constexpr (k >= KR::lo && k < KR::hi) {
+          const int y = rA + R2 * k;
+          v[k] = (y >= ylo && y <= yhi) ? in[(y - ylo) * B] : mk(0.0, 0.0);
+        } else {
+          v[k] = mk(0.0, 0.0);
+        }
       });
-      pass_a_in<R1, R2, true, KR::lo, KR::hi>(v, r, pd.tw2, Sb, B);
-      if (pair + 1 < p1) fetch(pair + 1);
+      pass_a_in<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, Sb, B);
     }
     __syncthreads();
+    if (tid == 0 && ny > 0 && pair + kStages < p1) {
+      mbar_expect_tx(&bar[st], tile_bytes);
+      bulk_g2s(ST + (size_t)st * tile_elems, src + (size_t)(pair + kStages) * t1_pair, tile_bytes, &bar[st]);
+    }
     if (r < R1) {
       cplx u[R2];
       pass_b<R1, R2, true>(u, r, Sb, B);
@@ -347,7 +484,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
         d[(size_t)(r + R1 * q) * pd.nzb * B] = u[q];
       });
     }
-    buf ^= 1;
+    if constexpr (XB == 1) __syncthreads();
+    if constexpr (C::ROT) {
+      rA += C::RPW;
+      if (rA >= RM) rA -= RM;
+    }
   }
 }
 
@@ -404,47 +545,20 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Staged variants of the y/z kernels ("bulk" kernels).  Where a block's input tile of one pair is
-// one contiguous run of memory (the band of a column set in T2, the rays of a plane in T1) it is
-// brought into a ring of KStages shared-memory stages by the TMA engine (bulk_g2s, one instruction
-// per tile issued by one thread) instead of per-thread register prefetches: the prefetch distance
-// is KStages pairs, no registers are held by in-flight loads and no per-element address arithmetic
-// is executed.  The twiddle table lives in shared memory too, so nothing inside the pair loop
-// waits on a global load.  Role rotation: the first radix pass only needs R2 of the max(R1,R2)
-// role rows of a block; which warp idles rotates with the pair index so that the four SM
-// sub-partitions carry the same FP64 load.
-// Shared memory: [2 exchange buffers N*B][twiddles N][KStages tiles][KStages mbarriers]
-// ---------------------------------------------------------------------------------------------
-constexpr int kStages = 2;
-
-template <int R1, int R2, int B>
-struct YZCfg {
-  static constexpr int N = R1 * R2;
-  static constexpr int RM = MaxOf<R1, R2>::v;
-  static constexpr int NT = B * RM;
-  static constexpr int RPW = 32 / B;  // role rows per warp
-  static constexpr bool ROT = (NT % 32 == 0) && (RM % RPW == 0) && (R2 < RM);
-  // bytes of dynamic shared memory for tiles of `tile_elems` complex numbers
-  static constexpr size_t smem(int tile_elems) {
-    return ((size_t)2 * N * B + N + (size_t)kStages * tile_elems) * sizeof(cplx) + kStages * sizeof(uint64_t);
-  }
-};
-
-// ---------------------------------------------------------------------------------------------
 // z pass of rhoofr: z-inverse FFT (band zero-padded to n3: putz, fftutil_utils.mod.F90:87-104)
 // fused with build_density_sum (density_utils.mod.F90:61-83).  The block keeps its rho tile in
 // registers over all pairs of the batch and does ONE read-modify-write of rho(r) per batch.
 // grid = (x tiles of the chunk, n2)
 // ---------------------------------------------------------------------------------------------
-template <int R1, int R2, int B, bool HALF>
-CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
+template <int R1, int R2, int B, bool HALF, int XB>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
     k_z_rho(const cplx* CPB_RESTRICT T2, double* rho, PlanDev pd, PairDev pr, int npair,
             int xt0) {
   using C = YZCfg<R1, R2, B>;
   constexpr int N = C::N, RM = C::RM, NT = C::NT;
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
-  cplx* TW = S + 2 * N * B;
+  cplx* TW = S + XB * N * B;
   cplx* ST = TW + N;
   const int tile_elems = pd.nzb * B;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ST + (size_t)kStages * tile_elems);
@@ -479,7 +593,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   int rA = r;  // role in the first radix pass (rotates by one warp per pair)
   for (int pair = 0; pair < npair; ++pair) {
     const int st = pair % kStages;
-    cplx* Sb = S + (pair & 1) * (N * B) + b;
+    cplx* Sb = S + (XB == 2 ? (pair & 1) : 0) * (N * B) + b;
     const double ca = __ldg(&pr.ca[pair]), cb = __ldg(&pr.cb[pair]);  // used after the barrier
     if (rA < R2) {
       mbar_wait(&bar[st], (unsigned)((pair / kStages) & 1));
@@ -509,6 +623,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
         acc[q] += ca * (u[q].x * u[q].x) + cb * (u[q].y * u[q].y);
       });
     }
+    if constexpr (XB == 1) __syncthreads();
     if constexpr (C::ROT) {
       rA += C::RPW;
       if (rA >= RM) rA -= RM;
@@ -533,9 +648,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
 template <int R1, int R2, int B, bool HALF>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     k_z_vpsi(cplx* T2, const double* CPB_RESTRICT vpot, PlanDev pd, int xt0, int npair, int ppg) {
-  constexpr int N = R1 * R2;
+  using C = YZCfg<R1, R2, B>;
+  constexpr int N = C::N, RM = C::RM, NT = C::NT;
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
+  cplx* TW = S + 2 * N * B;
+  cplx* ST = TW + N;
+  const int tile_elems = pd.nzb * B;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ST + (size_t)kStages * tile_elems);
+  const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(cplx));
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
   const int xtc = blockIdx.x, nxc = gridDim.x;
@@ -545,37 +666,51 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
   const bool xok = x < pd.n1;
   const size_t pstride = (size_t)nxc * pd.n2 * pd.nzb * B;
-  cplx* tile = T2 + ((size_t)xtc * pd.n2 + y) * pd.nzb * B + b;
+  cplx* tile = T2 + ((size_t)xtc * pd.n2 + y) * pd.nzb * B;
   const int zlo = pd.zlo, nzb = pd.nzb;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < N; i += NT) TW[i] = pd.tw3[i];
   double vv[R2];
   static_for<0, R2>([&](auto qq) {
     constexpr int q = decltype(qq)::value;
     vv[q] = (r < R1 && xok) ? __ldg(&vpot[((size_t)(r + R1 * q) * pd.kr2 + y) * pd.kr1 + x]) : 0.0;
   });
-  cplx nv[KR::cnt];
-  auto fetch = [&](int pair) {
-    const cplx* s = tile + (size_t)pair * pstride;
-    static_for<0, KR::cnt>([&](auto kk) {
-      constexpr int k = KR::lo + decltype(kk)::value;
-      const int zr = r + R2 * k - zlo;
-      nv[decltype(kk)::value] = (zr >= 0 && zr < nzb) ? s[zr * B] : mk(0.0, 0.0);
-    });
-  };
-  if (r < R2 && p0 < p1) fetch(p0);
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kStages && p0 + s < p1; ++s) {
+      mbar_expect_tx(&bar[s], tile_bytes);
+      bulk_g2s(ST + (size_t)s * tile_elems, tile + (size_t)(p0 + s) * pstride, tile_bytes, &bar[s]);
+    }
+  }
   cplx* Sa = S + b;            // exchange buffer of the inverse transform
   cplx* Sf = S + N * B + b;    // exchange buffer of the forward transform
+  int rA = r;  // role in the band-side radix passes (rotates by one warp per pair)
   for (int pair = p0; pair < p1; ++pair) {
-    if (r < R2) {
+    const int it = pair - p0;
+    const int st = it % kStages;
+    if (rA < R2) {
+      mbar_wait(&bar[st], (unsigned)((it / kStages) & 1));
+      const cplx* in = ST + (size_t)st * tile_elems + b;
       cplx v[R1];
       static_for<0, R1>([&](auto kk) {
         constexpr int k = decltype(kk)::value;
-        if constexpr (k >= KR::lo && k < KR::hi) v[k] = nv[k - KR::lo];
-        else v[k] = mk(0.0, 0.0);
+        if constexpr (k >= KR::lo && k < KR::hi) {
+          const int zr = rA + R2 * k - zlo;
+          v[k] = (zr >= 0 && zr < nzb) ? in[zr * B] : mk(0.0, 0.0);
+        } else {
+          v[k] = mk(0.0, 0.0);
+        }
       });
-      pass_a_in<R1, R2, true, KR::lo, KR::hi>(v, r, pd.tw3, Sa, B);
-      if (pair + 1 < p1) fetch(pair + 1);
+      pass_a_in<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, Sa, B);
     }
     __syncthreads();
+    if (tid == 0 && pair + kStages < p1) {
+      mbar_expect_tx(&bar[st], tile_bytes);
+      bulk_g2s(ST + (size_t)st * tile_elems, tile + (size_t)(pair + kStages) * pstride, tile_bytes, &bar[st]);
+    }
     if (r < R1) {
       cplx u[R2];
       pass_b<R1, R2, true>(u, r, Sa, B);
@@ -584,18 +719,22 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
         u[q].x *= vv[q];
         u[q].y *= vv[q];
       });
-      pass_a<R2, R1, false>(u, r, pd.tw3, Sf, B);
+      pass_a<R2, R1, false, true>(u, r, TW, Sf, B);
     }
     __syncthreads();
-    if (r < R2) {
+    if (rA < R2) {
       cplx w[R1];
-      pass_b<R2, R1, false>(w, r, Sf, B);
-      cplx* d = tile + (size_t)pair * pstride;
+      pass_b<R2, R1, false>(w, rA, Sf, B);
+      cplx* d = tile + (size_t)pair * pstride + b;
       static_for<KR::lo, KR::hi>([&](auto kk) {
         constexpr int k = decltype(kk)::value;
-        const int zr = r + R2 * k - zlo;
+        const int zr = rA + R2 * k - zlo;
         if (zr >= 0 && zr < nzb) d[zr * B] = w[k];
       });
+    }
+    if constexpr (C::ROT) {
+      rA += C::RPW;
+      if (rA >= RM) rA -= RM;
     }
   }
 }

@@ -66,48 +66,8 @@ CPB_GLOBAL k_sum(const double* CPB_RESTRICT a, size_t n, double* CPB_RESTRICT pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_pack: set_psi_2_states_g / set_psi_1_state_g (state_utils.mod.F90:132-189) into the band-ray
-// storage G[pair][xb][ray] (see kernels.h):  G(+G) = c1 + i c2,  G(-G) = conj(c1) + i conj(c2),
-// G = 0 written once (state_utils.mod.F90:187).  Positions that hold no plane wave are never
-// written by any kernel and stay zero from plan creation (the reference zeroes psi per pair,
-// rhoofr_utils.mod.F90:328, vpsi_utils.mod.F90:428).  One thread = one plane wave, looping over
-// the pairs of its group; c0 is read fully coalesced, the 16-byte scatter lands in L2.
-// grid = (ceil(ngw/256), pair groups), block = 256
-// ---------------------------------------------------------------------------------------------
-constexpr int kPackUnroll = 4;
-
-CPB_GLOBAL k_pack(const cplx* CPB_RESTRICT c0, long ldc, cplx* CPB_RESTRICT G, PlanDev pd, PairDev pr,
-                  int npair, int ppg) {
-  const int ig = blockIdx.x * 256 + threadIdx.x;
-  if (ig >= pd.ngw) return;
-  const int p0 = blockIdx.y * ppg;
-  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
-  const uint32_t lp = pd.gpos[ig], lm = pd.gneg[ig];
-  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
-  for (int q0 = p0; q0 < p1; q0 += kPackUnroll) {
-    cplx a[kPackUnroll], b[kPackUnroll];
-    static_for<0, kPackUnroll>([&](auto jj) {
-      constexpr int j = decltype(jj)::value;
-      if (q0 + j < p1) {
-        const int s1 = pr.st1[q0 + j], s2 = pr.st2[q0 + j];
-        a[j] = c0[(size_t)s1 * ldc + ig];
-        b[j] = (s2 >= 0) ? c0[(size_t)s2 * ldc + ig] : mk(0.0, 0.0);
-      }
-    });
-    static_for<0, kPackUnroll>([&](auto jj) {
-      constexpr int j = decltype(jj)::value;
-      if (q0 + j < p1) {
-        cplx* g = G + (size_t)(q0 + j) * g_pair;
-        g[lp] = mk(a[j].x - b[j].y, a[j].y + b[j].x);                // c1 + i c2
-        if (lm != lp) g[lm] = mk(a[j].x + b[j].y, b[j].x - a[j].y);  // conj(c1) + i conj(c2)
-      }
-    });
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // k_unpack: vpsi_utils.mod.F90:626-673 + add_wfn (:717).  Reads FFT[V psi] at +G and -G from the
-// band-ray storage (already scaled by 1/N in k_x_fwd), separates the two states, adds the
+// band-ray storage G (kernels.h; already scaled by 1/N in k_x_fwd), separates the two states, adds the
 // kinetic term, scales by -f/2 and updates c2.  ACC: c2 += result (reference semantics);
 // !ACC: c2 = result.  grid = (ceil(ngw/256), pair groups), block = 256
 // ---------------------------------------------------------------------------------------------

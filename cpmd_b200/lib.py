@@ -73,7 +73,7 @@ SYMBOLS = {
     "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
 }
 
-KERNEL_KINDS = ("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd", "kin_energy", "rho_sum", "pack", "unpack")
+KERNEL_KINDS = ("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd", "kin_energy", "rho_sum", "unpack")
 
 
 def declare(cdll: C.CDLL) -> C.CDLL:

@@ -143,7 +143,7 @@ long cpb_plan_launch_count(const cpb_plan* plan);
  * the roofline of the dominant kernel; the counterpart of the reference's tiset/tihalt timers
  * around invfftn/fwfftn/vpsi/rhoofr (timer.mod.F90:39-233). */
 enum {
-  CPB_K_X_INV = 0, /* x inverse                */
+  CPB_K_X_INV = 0, /* gather + pack + x inverse */
   CPB_K_Y_INV = 1,
   CPB_K_Z_RHO = 2, /* z inverse + density      */
   CPB_K_Z_VPSI = 3, /* z inverse * V * z forward */
@@ -151,9 +151,8 @@ enum {
   CPB_K_X_FWD = 5, /* x forward (scaled)       */
   CPB_K_KIN = 6,
   CPB_K_SUM = 7,
-  CPB_K_PACK = 8,   /* set_psi_2_states_g -> band-ray storage        */
-  CPB_K_UNPACK = 9, /* unpack + kinetic term + occupation + c2 update */
-  CPB_NKINDS = 10
+  CPB_K_UNPACK = 8, /* unpack + kinetic term + occupation + c2 update */
+  CPB_NKINDS = 9
 };
 int cpb_plan_set_profiling(cpb_plan* plan, int on);
 int cpb_plan_get_kernel_times(cpb_plan* plan, double* ms /*[CPB_NKINDS]*/, long* counts /*[CPB_NKINDS]*/,
