@@ -2,7 +2,7 @@
 """Benchmark of the vpsi + rhoofr hot path (BASELINE.json metric: band-FFTs/s, FP64).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--mesh 192] [--states 512] [--batch 16]
+                    [--mesh 192] [--states 512] [--batch 32]
 
 One "step" = one Car-Parrinello electronic step of the hot path over all states:
 rhoofr (all pairs) -> cp_grp_redist(rho) [N>1] -> V broadcast [N>1] -> vpsi (all pairs);
@@ -280,8 +280,11 @@ def run_ours(args, rank, world, local):
     dom_ms, dom_n = ktimes[dom]
     npairs_local = (cnt + 1) // 2
     pairs_per_launch = npairs_local * args.steps / max(dom_n, 1) * (2 if dom in ("x_inv", "y_inv") else 1)
+    # algorithmic bytes per packed pair of each kernel: x_inv reads the two c0 columns
+    # and writes T1; x_fwd reads T1 (its band-ray output stays in L2 for k_unpack, which is charged
+    # the c0 read, the c2 read-modify-write: 4C)
     per_pair = {"x_inv": 2 * bm["C"] + bm["Sx"], "y_inv": bm["Sx"] + bm["Sy"], "z_rho": bm["Sy"],
-                "z_vpsi": 2 * bm["Sy"], "y_fwd": bm["Sy"] + bm["Sx"], "x_fwd": bm["Sx"] + 4 * bm["C"]}[dom]
+                "z_vpsi": 2 * bm["Sy"], "y_fwd": bm["Sy"] + bm["Sx"], "x_fwd": bm["Sx"]}[dom]
     per_launch_extra = bm["N8"] if dom in ("z_rho", "z_vpsi") else 0.0
     bytes_per_launch = pairs_per_launch * per_pair + per_launch_extra
     achieved = bytes_per_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
@@ -316,7 +319,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", type=int, default=192)
     ap.add_argument("--states", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sample-states", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

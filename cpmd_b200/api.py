@@ -62,7 +62,7 @@ def _is_torch(a):
 class Plan:
     """One FFT/G-vector plan on one GPU (``cpb_plan_create``)."""
 
-    def __init__(self, nr, inyh, hg, tpiba2=1.0, omega=1.0, kr=None, device=0, max_batch=16, _cdll=None):
+    def __init__(self, nr, inyh, hg, tpiba2=1.0, omega=1.0, kr=None, device=0, max_batch=32, _cdll=None):
         self._L = _cdll if _cdll is not None else _lib.load()
         self._h = C.c_void_p()
         nr = tuple(int(v) for v in nr)
@@ -256,7 +256,7 @@ class CpmdContext:
     cp_nogrp: int = 1                 # parai%cp_nogrp
     cp_inter_me: int = 0              # parai%cp_inter_me
     device: int = 0
-    max_batch: int = 16
+    max_batch: int = 32
     # variant switches (must all be off; otherwise the shim falls back to the original routine)
     tkpnt: bool = False               # tkpts%tkpnt
     tlsd: bool = False                # cntl%tlsd

@@ -74,7 +74,8 @@ void y_inv_t(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int n
   auto k = k_y_inv<R1, R2, B, HALF, CPB_YINV_XB>;
   const size_t smem = YZCfg<R1, R2, B>::smem(pd.nyb * B, CPB_YINV_XB);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T1, T2, pd, xt0, npair, ppg);
+  CPB_LAUNCH(k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
+             dim3(B * RM), smem, st, T1, T2, pd, xt0, npair, ppg);
 }
 void y_inv(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
            bool half) {
@@ -86,7 +87,8 @@ template <bool HALF>
 void y_fwd_t(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg) {
   auto k = k_y_fwd<R1, R2, B, HALF>;
   allow_smem(k, kSmemYZ2);
-  CPB_LAUNCH(k, dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg), dim3(B * RM), kSmemYZ2, st, T2, T1, pd, xt0, npair, ppg);
+  CPB_LAUNCH(k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
+             dim3(B * RM), kSmemYZ2, st, T2, T1, pd, xt0, npair, ppg);
 }
 void y_fwd(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
            bool half) {

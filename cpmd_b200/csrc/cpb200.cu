@@ -70,11 +70,11 @@ struct cpb_plan {
   int geq0 = 0;
   double tpiba2 = 0, omega = 0;
   int device = 0;
-  int max_batch = 16;
+  int max_batch = 32;
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
-  int x_sub = 4;          // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
+  int x_sub = 8;          // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
@@ -541,7 +541,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->tpiba2 = tpiba2;
     p->omega = omega;
     p->device = device;
-    p->max_batch = std::min(max_batch_pairs > 0 ? max_batch_pairs : 16, (int)kMaxGroup);
+    p->max_batch = std::min(max_batch_pairs > 0 ? max_batch_pairs : 32, (int)kMaxGroup);
     p->kx = find_axis_kernels(nr[0]);
     p->ky = find_axis_kernels(nr[1]);
     p->kz = find_axis_kernels(nr[2]);

@@ -384,6 +384,9 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD
 // 128-register budget) lets a fourth block share the SM.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStages = 2;
+#ifndef CPB_Y_ZFAST
+#define CPB_Y_ZFAST 1
+#endif
 #ifndef CPB_ZRHO_XB
 #define CPB_ZRHO_XB 2
 #endif
@@ -427,8 +430,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
   uint64_t* bar = reinterpret_cast<uint64_t*>(ST + (size_t)kStages * tile_elems);
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
+#if CPB_Y_ZFAST
+  // z plane is the fastest-varying block coordinate: blocks that run at the same time touch
+  // adjacent 128-byte rows of T2, which L2 merges into full DRAM pages
+  const int zr = blockIdx.x;
+  const int xtc = blockIdx.y, nxc = gridDim.y;
+#else
   const int xtc = blockIdx.x, nxc = gridDim.x;
   const int zr = blockIdx.y;
+#endif
   const int p0 = blockIdx.z * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
   const int ylo = pd.ylo[zr], yhi = pd.yhi[zr];
@@ -501,8 +511,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   CPB_DYN_SMEM(cplx, S);
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
+#if CPB_Y_ZFAST
+  // z plane is the fastest-varying block coordinate: blocks that run at the same time touch
+  // adjacent 128-byte rows of T2, which L2 merges into full DRAM pages
+  const int zr = blockIdx.x;
+  const int xtc = blockIdx.y, nxc = gridDim.y;
+#else
   const int xtc = blockIdx.x, nxc = gridDim.x;
   const int zr = blockIdx.y;
+#endif
   const int p0 = blockIdx.z * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
   const int ylo = pd.ylo[zr], yhi = pd.yhi[zr];

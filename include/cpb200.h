@@ -89,7 +89,7 @@ const char* cpb_version(void);
 int cpb_length_supported(int n);
 
 /* nr, kr: 3 ints each.  inyh: (3,ngw) column-major INTEGER*4, 1-based (cppt inyh).  hg: |G|^2 in
- * units of tpiba2.  device: CUDA ordinal.  max_batch_pairs: pairs per batch (<=0: default 16). */
+ * units of tpiba2.  device: CUDA ordinal.  max_batch_pairs: pairs per batch (<=0: default 32). */
 int cpb_plan_create(cpb_plan** plan, const int* nr, const int* kr, int ngw, const int32_t* inyh,
                     const double* hg, double tpiba2, double omega, int device,
                     int max_batch_pairs);
