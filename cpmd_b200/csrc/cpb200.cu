@@ -373,11 +373,11 @@ struct BatchHooks {
   virtual ~BatchHooks() {}
 };
 
-void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const std::vector<PairHost>& pairs_in,
-                const std::vector<double>& fa_in, const std::vector<double>& fb_in, double* rho,
+// `pr`: the call's pair descriptors, already uploaded (upload_pairs) - the host-pointer entry points
+// do that BEFORE they enqueue their bulk H2D copies, because the copy engine serves all streams in
+// FIFO order and the first kernel would otherwise wait behind the whole upload.
+void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, double* rho,
                 cudaStream_t st, BatchHooks* hooks) {
-  PairDev pr = upload_pairs(p, pairs_in, fa_in, fb_in, st);
-  const int np = (int)pairs_in.size();
   int b = 0;
   for (int off = 0; off < np; off += p->max_batch, ++b) {
     const int nb = std::min(p->max_batch, np - off);
@@ -395,11 +395,8 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const std::vector<PairHos
   rt::check_last("rhoofr kernels");
 }
 
-void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const std::vector<PairHost>& pairs,
-              const std::vector<double>& fi, const std::vector<double>& fip1, const double* vpot,
+void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, const double* vpot,
               bool accumulate, cudaStream_t st, BatchHooks* hooks) {
-  PairDev pr = upload_pairs(p, pairs, fi, fip1, st);
-  const int np = (int)pairs.size();
   int b = 0;
   for (int off = 0; off < np; off += p->max_batch, ++b) {
     const int nb = std::min(p->max_batch, np - off);
@@ -839,7 +836,7 @@ int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, cons
     ensure_red(p, kRedPerState * nblk + kSumBlocks);
     rt::dzero(rhoe_dev, p->nnr1() * sizeof(double), st);  // rhoofr_utils.mod.F90:198
     launch_kin(p, c0, ld_c0, first, nblk, st);               // :178
-    run_rhoofr(p, c0, ld_c0, pairs, ca, cb, rhoe_dev, st, nullptr);
+    run_rhoofr(p, c0, ld_c0, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), rhoe_dev, st, nullptr);
     launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + kRedPerState * nblk, st);  // :607-619
     rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + kSumBlocks) * sizeof(double), st);
     rt::sync(st);
@@ -868,7 +865,7 @@ int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nst
     std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups);
     std::vector<double> fi, fip1;
     vpsi_coefs(pairs, f, (flags & CPB_VPSI_TKSHAM) != 0, fi, fip1);
-    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, pairs, fi, fip1, vpot_dev,
+    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, fip1, st), (int)pairs.size(), vpot_dev,
              !(flags & CPB_VPSI_OVERWRITE), st, nullptr);
     rt::sync(st);
     resolve_spans(p);
