@@ -44,6 +44,21 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _measured_traffic(kernel):
+    """DRAM bytes per packed pair of `kernel` from the newest committed ncu --set full capture
+    (profiles/*_traffic.json, written by tools/ncu_traffic.py); None if there is none."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            k = json.load(open(path))["kernels"].get(kernel)
+        except Exception:
+            k = None
+        if k:
+            best = (float(k["dram_bytes_per_pair"]), os.path.relpath(path, ROOT))
+    return best
+
+
 def _byte_model(info, nstate):
     """Algorithmic bytes (SURVEY 8d / DESIGN.md): C=16 ngw, S_x=16 n1 rays, S_y=16 n1 n2 zband."""
     n1, n2, n3 = info["nr"]
@@ -161,7 +176,7 @@ def cpu_baseline(args):
 
     cores = staged.set_threads(0)
     n = args.mesh
-    ns = args.ref_sample_states
+    ns = min(args.cpu_sample_states, args.states)
     geo = orc.make_geometry(n)
     c0, f, v = orc.synthetic_inputs(geo, ns, seed=1234 + n + 7 * args.states)
     c2 = np.zeros_like(c0)
@@ -236,19 +251,29 @@ def run_ours(args, rank, world, local):
             ms = t.item()
         return ms / steps
 
-    # ---- device-resident timing (value), with per-kernel CUDA-event timing for the roofline
+    # ---- device-resident timing (value): the product configuration, no per-kernel events inside the
+    # timed region
     sampler = ClockSampler(local) if rank == 0 else None
-    plan.set_profiling(True)
     for _ in range(args.warmup):
         step_device()
-    plan.kernel_times(reset=True)
     l0 = plan.launch_count
     ms_step = timed(step_device, args.steps, 0)
     launches = plan.launch_count - l0
-    ktimes = plan.kernel_times(reset=True)
-    plan.set_profiling(False)
     clocks = sampler.stop() if sampler else None
     value = 3.0 * nstate / (ms_step * 1e-3)
+
+    # ---- per-kernel durations for the roofline: a separate pass with the kernels serialised on one
+    # stream (cpb_plan_set_streams(1)) and every launch bracketed by CUDA events on that stream
+    prof_steps = max(1, min(args.steps, 2))
+    n_streams = info["streams"]
+    plan.set_streams(1)
+    plan.set_profiling(True)
+    step_device()
+    plan.kernel_times(reset=True)
+    ms_step_serial = timed(step_device, prof_steps, 0)
+    ktimes = plan.kernel_times(reset=True)
+    plan.set_profiling(False)
+    plan.set_streams(n_streams)
 
     # ---- e2e through the host-pointer C ABI (what the Fortran shim binds)
     def step_host():
@@ -262,6 +287,20 @@ def run_ours(args, rank, world, local):
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ms_e2e = timed(step_host, e2e_steps, 1)
+
+    # the same step as the MD driver issues it: forces_driver.mod.F90:175 zeroes c2 immediately
+    # before CALL vpsi (:224), so a shim at that call site may pass CPB_VPSI_OVERWRITE and skip the
+    # upload of the zeros (reported separately; the headline e2e keeps the subroutine's += semantics)
+    def step_host_ow():
+        plan.rhoofr(c0_block_host, f_block, rho_host, flags=lib.CPB_C0_KEEP)
+        if world > 1:
+            rho.copy_(rho_host, non_blocking=True)
+            cdist.cp_grp_redist(rho)
+            rho_host.copy_(rho, non_blocking=True)
+            torch.cuda.synchronize()
+        plan.vpsi(c0_block_host, c2_block_host, f_block, v_host, flags=lib.CPB_C0_REUSE | lib.CPB_VPSI_OVERWRITE)
+
+    ms_e2e_ow = timed(step_host_ow, e2e_steps, 1)
     blk_bytes = cnt * plan.ngw * 16
     h2d = blk_bytes * 2 + plan.nnr1 * 8          # c0 block (once, kept for vpsi) + c2 block (+=) + V
     d2h = blk_bytes + plan.nnr1 * 8              # c2 block + rho
@@ -279,7 +318,7 @@ def run_ours(args, rank, world, local):
     tot_ms = sum(v_[0] for v_ in ktimes.values())
     dom_ms, dom_n = ktimes[dom]
     npairs_local = (cnt + 1) // 2
-    pairs_per_launch = npairs_local * args.steps / max(dom_n, 1) * (2 if dom in ("x_inv", "y_inv") else 1)
+    pairs_per_launch = npairs_local * prof_steps / max(dom_n, 1) * (2 if dom in ("x_inv", "y_inv") else 1)
     # algorithmic bytes per packed pair of each kernel: x_inv reads the two c0 columns
     # and writes T1; x_fwd reads T1 (its band-ray output stays in L2 for k_unpack, which is charged
     # the c0 read, the c2 read-modify-write: 4C)
@@ -288,6 +327,8 @@ def run_ours(args, rank, world, local):
     per_launch_extra = bm["N8"] if dom in ("z_rho", "z_vpsi") else 0.0
     bytes_per_launch = pairs_per_launch * per_pair + per_launch_extra
     achieved = bytes_per_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
+    mt = _measured_traffic("k_" + dom)
+    traffic = mt[0] * pairs_per_launch if mt else None
     step_bytes = _byte_model(info, nstate)["step"] / world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -297,14 +338,23 @@ def run_ours(args, rank, world, local):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "steps": e2e_steps,
                 "api": "cpb_rhoofr(CPB_C0_KEEP) + cpb_vpsi(CPB_C0_REUSE), pinned host buffers, c2 += semantics"},
+        "e2e_overwrite": {"value": 3.0 * nstate / (ms_e2e_ow * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_ow,
+                          "h2d_bytes_per_step": int(h2d - blk_bytes), "d2h_bytes_per_step": int(d2h),
+                          "api": "as e2e, but cpb_vpsi(CPB_VPSI_OVERWRITE): the MD call site zeroes c2 first "
+                                 "(forces_driver.mod.F90:175,224)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": (mt[1] + " (dram bytes per pair x pairs per launch)") if mt else None,
+                     "peak_source": peak_src,
                      "bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms / max(dom_n, 1),
                      "kernel_share_of_step": dom_ms / max(tot_ms, 1e-9),
                      "step_algorithmic_GB": step_bytes / 1e9,
                      "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
-                     "kernel_ms_per_step": {k: v_[0] / args.steps for k, v_ in ktimes.items()}},
+                     "timing": "kernels serialised on one stream, CUDA events around every launch, "
+                               f"{prof_steps} step(s); the timed `value` run uses {n_streams} batch stream(s), no events",
+                     "ms_per_step_serialised": ms_step_serial,
+                     "kernel_ms_per_step": {k: v_[0] / prof_steps for k, v_ in ktimes.items()}},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
@@ -321,7 +371,10 @@ def main():
     ap.add_argument("--states", type=int, default=512)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sample-states", type=int, default=8)
+    ap.add_argument("--ref-sample-states", type=int, default=96,
+                    help="states per step of the --impl reference arm (bounded sample of the workload)")
+    ap.add_argument("--cpu-sample-states", type=int, default=512,
+                    help="states of the cpu_baseline leg (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -108,7 +108,7 @@ class Plan:
                     zband=inf.zband, xband=inf.xband, max_batch=inf.max_batch, device=inf.device,
                     radix=tuple((inf.radix[d][0], inf.radix[d][1]) for d in range(3)),
                     workspace_bytes=inf.workspace_bytes,
-                    band_pruned=tuple(inf.band_pruned), chunk_xtiles=inf.chunk_xtiles)
+                    band_pruned=tuple(inf.band_pruned), chunk_xtiles=inf.chunk_xtiles, streams=inf.streams)
 
     def maps(self):
         """(nzhs, indzs) with the reference's numbering (fftprp_utils.mod.F90:269-285)."""
@@ -123,6 +123,10 @@ class Plan:
 
     def set_profiling(self, on=True):
         self._check(self._L.cpb_plan_set_profiling(self._h, int(bool(on))))
+
+    def set_streams(self, n):
+        """Number of work spaces/streams the batches of a call alternate between (1 = serialised)."""
+        self._check(self._L.cpb_plan_set_streams(self._h, int(n)))
 
     def kernel_times(self, reset=False):
         """{kernel class: (total ms, launches)} accumulated while profiling was on."""

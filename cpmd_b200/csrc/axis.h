@@ -33,6 +33,7 @@ struct AxisKernels {
   void (*z_vpsi)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
                  int ppg, bool half);
   int yz_blocks_per_sm;  // occupancy the y/z kernels are compiled for
+  int x_inv_blocks, x_fwd_blocks;  // same for the x kernels
 };
 
 const AxisKernels* find_axis_kernels(int n);

@@ -125,7 +125,8 @@ void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, in
 }
 
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
-                            x_inv, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, YZBlocks<R1, R2>::v};
+                            x_inv, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, YZBlocks<R1, R2>::v,
+                            XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD};
 
 }  // namespace
 

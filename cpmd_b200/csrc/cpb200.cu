@@ -74,7 +74,7 @@ struct cpb_plan {
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
-  int x_sub = 8;          // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
+  int x_sub = 16;         // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
@@ -88,8 +88,19 @@ struct cpb_plan {
   uint32_t *d_gpos = nullptr, *d_gneg = nullptr, *d_gtab = nullptr;
   double* d_hg = nullptr;
   cplx *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw3 = nullptr;
-  cplx *T1 = nullptr, *T2 = nullptr;
-  cplx *G = nullptr;   // band-ray storage of one x_sub sub-batch (written by k_x_fwd, read by k_unpack)
+  // Work spaces.  Consecutive batches of a call alternate between kNumWS work spaces, each with
+  // its own stream: the HBM-bound x/y kernels of one batch overlap the FP64-bound z kernel of the
+  // other, and the tail of every launch is filled by the next one.
+  struct WorkSpace {
+    cplx *T1 = nullptr, *T2 = nullptr;
+    cplx* G = nullptr;  // band-ray storage of one x_sub sub-batch (written by k_x_fwd, read by k_unpack)
+    cudaStream_t s = nullptr;
+    rt::event_t ev_join = nullptr, ev_rho = nullptr;
+  };
+  static constexpr int kNumWS = 2;
+  WorkSpace ws[kNumWS];
+  int nws = 1;  // work spaces in use (default 1: on B200 the overlap costs vpsi more than it gains; CPB_STREAMS=2)
+  rt::event_t ev_fork = nullptr;
   size_t workspace_bytes = 0;
   // per-call pair descriptors
   int pair_cap = 0;
@@ -138,13 +149,19 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_gpos);
   rt::dfree(p->d_gneg);
   rt::dfree(p->d_gtab);
-  rt::dfree(p->G);
   rt::dfree(p->d_hg);
   rt::dfree(p->d_tw1);
   rt::dfree(p->d_tw2);
   rt::dfree(p->d_tw3);
-  rt::dfree(p->T1);
-  rt::dfree(p->T2);
+  for (auto& w : p->ws) {
+    rt::dfree(w.T1);
+    rt::dfree(w.T2);
+    rt::dfree(w.G);
+    rt::stream_destroy(w.s);
+    rt::event_destroy(w.ev_join);
+    rt::event_destroy(w.ev_rho);
+  }
+  rt::event_destroy(p->ev_fork);
   rt::dfree(p->d_st1);
   rt::dfree(p->d_st2);
   rt::dfree(p->d_ca);
@@ -294,15 +311,29 @@ void resolve_spans(cpb_plan* p) {
   p->spans.clear();
 }
 
-// pairs each block of a y/z kernel loops over: as many as possible (longer prefetch pipelines)
-// while the grid still holds ~2 full waves of blocks
-int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group) {
-  const int target = 2 * p->n_sm * 3;
-  int groups = (target + blocks_per_pair_group - 1) / std::max(blocks_per_pair_group, 1);
-  groups = std::max(1, std::min(groups, npair));
-  return (npair + groups - 1) / groups;
+// Pairs each block of an FFT kernel loops over.  A launch has `blocks_per_pair_group` blocks per
+// group of pairs and the SM array holds `slots` blocks at a time, so the launch runs in
+// ceil(blocks / slots) waves, each lasting (pairs per block + block prologue) pair-times: pick the
+// group count that minimises that product.  Longer loops amortise the prologue and keep the
+// prefetch pipeline full; more groups cut the cost of the last, partially filled wave.
+int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group, int blocks_per_sm,
+                    double prologue = 0.5) {
+  const long slots = (long)p->n_sm * std::max(blocks_per_sm, 1);
+  int best = npair;
+  double best_cost = 1e300;
+  for (int groups = 1; groups <= npair; ++groups) {
+    const int ppg = (npair + groups - 1) / groups;
+    const int g = (npair + ppg - 1) / ppg;  // groups actually launched
+    const long blocks = (long)blocks_per_pair_group * g;
+    const long waves = (blocks + slots - 1) / slots;
+    const double cost = (double)waves * (ppg + prologue);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = ppg;
+    }
+  }
+  return best;
 }
-
 
 // pair groups for the elementwise G-space kernels: enough blocks to fill the machine a few times
 int ew_ppg(const cpb_plan* p, int npair, int waves) {
@@ -312,52 +343,36 @@ int ew_ppg(const cpb_plan* p, int npair, int waves) {
   return (npair + groups - 1) / groups;
 }
 
-// pairs per block of the inverse x pass: long enough loops to amortise the block prologue while the
-// grid still fills the machine several times (the last, partial wave costs 1/waves of the time)
-int x_inv_ppg(const cpb_plan* p, int npair) {
-  const int tiles = p->nrp / p->kx->sl;
-  const int slots = p->n_sm * 4;
-  int best = 1;
-  double best_cost = 1e30;
-  for (int ppg = 1; ppg <= std::min(npair, 8); ++ppg) {
-    const long blocks = (long)tiles * ((npair + ppg - 1) / ppg);
-    const long waves = (blocks + slots - 1) / slots;
-    const double cost = (double)waves * (ppg + 0.5);  // 0.5 pair-times of prologue per block
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = ppg;
-    }
-  }
-  return best;
-}
-
 // x pass, inverse: one launch per batch; the kernel gathers the coefficients from c0 itself
-void run_x_inv(cpb_plan* p, const cplx* c0, long ldc, const PairDev& prb, int nb, cudaStream_t st) {
+void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb) {
+  cudaStream_t st = w.s;
   Timed t(p, st, CPB_K_X_INV);
-  p->kx->x_inv(st, c0, ldc, p->T1, p->pd, prb, nb, x_inv_ppg(p, nb), p->half_x);
+  p->kx->x_inv(st, c0, ldc, w.T1, p->pd, prb, nb, pairs_per_group(p, nb, p->nrp / p->kx->sl, p->kx->x_inv_blocks),
+               p->half_x);
 }
 
 // x pass, forward, in sub-batches of x_sub pairs: k_x_fwd writes the sub-batch's band-ray storage
 // (it stays in L2), k_unpack gathers +G / -G from it and updates c2.
-void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb, bool accumulate,
-               cudaStream_t st) {
+void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb,
+               bool accumulate) {
+  cudaStream_t st = w.s;
   for (int o = 0; o < nb; o += p->x_sub) {
     const int ns = std::min(p->x_sub, nb - o);
     PairDev prs = offset_pairs(prb, o);
     {
       Timed t(p, st, CPB_K_X_FWD);
-      p->kx->x_fwd(st, p->T1 + (size_t)o * p->t1_pair, p->G, p->pd, ns,
-                   pairs_per_group(p, ns, p->nrp / p->kx->sl), p->half_x);
+      p->kx->x_fwd(st, w.T1 + (size_t)o * p->t1_pair, w.G, p->pd, ns,
+                   pairs_per_group(p, ns, p->nrp / p->kx->sl, p->kx->x_fwd_blocks), p->half_x);
     }
     Timed t(p, st, CPB_K_UNPACK);
     const int ppg = ew_ppg(p, ns, 8);
     const dim3 grid((p->ngw + 255) / 256, (ns + ppg - 1) / ppg);
     if (accumulate) {
       auto k = k_unpack<true>;
-      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->G, c0, c2, ldc, p->pd, prs, ns, ppg);
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)w.G, c0, c2, ldc, p->pd, prs, ns, ppg);
     } else {
       auto k = k_unpack<false>;
-      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)p->G, c0, c2, ldc, p->pd, prs, ns, ppg);
+      CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)w.G, c0, c2, ldc, p->pd, prs, ns, ppg);
     }
   }
 }
@@ -368,51 +383,74 @@ void run_x_fwd(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& p
 // that batch's H2D).
 // ------------------------------------------------------------------------------------------
 struct BatchHooks {
-  virtual void before_batch(int /*b*/, int /*pair0*/, int /*np*/) {}
-  virtual void after_batch(int /*b*/, int /*pair0*/, int /*np*/) {}
+  // called before / after the kernels of batch b are enqueued on stream `st`
+  virtual void before_batch(int /*b*/, int /*pair0*/, int /*np*/, cudaStream_t /*st*/) {}
+  virtual void after_batch(int /*b*/, int /*pair0*/, int /*np*/, cudaStream_t /*st*/) {}
   virtual ~BatchHooks() {}
 };
+
+// fork the work-space streams off the caller's stream / join them back
+void fork_streams(cpb_plan* p, cudaStream_t st, int nbatches) {
+  rt::event_record(p->ev_fork, st);
+  for (int i = 0; i < std::min(p->nws, nbatches); ++i) rt::stream_wait(p->ws[i].s, p->ev_fork);
+}
+void join_streams(cpb_plan* p, cudaStream_t st, int nbatches) {
+  for (int i = 0; i < std::min(p->nws, nbatches); ++i) {
+    rt::event_record(p->ws[i].ev_join, p->ws[i].s);
+    rt::stream_wait(st, p->ws[i].ev_join);
+  }
+}
 
 // `pr`: the call's pair descriptors, already uploaded (upload_pairs) - the host-pointer entry points
 // do that BEFORE they enqueue their bulk H2D copies, because the copy engine serves all streams in
 // FIFO order and the first kernel would otherwise wait behind the whole upload.
 void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, double* rho,
                 cudaStream_t st, BatchHooks* hooks) {
+  const int nbatches = (np + p->max_batch - 1) / p->max_batch;
+  fork_streams(p, st, nbatches);
   int b = 0;
   for (int off = 0; off < np; off += p->max_batch, ++b) {
     const int nb = std::min(p->max_batch, np - off);
-    if (hooks) hooks->before_batch(b, off, nb);
+    cpb_plan::WorkSpace& w = p->ws[b % p->nws];
+    if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
-    run_x_inv(p, c0, ldc, prb, nb, st);
-    // y and z passes chunk by chunk of x tiles: the chunk's T2 stays in L2
+    run_x_inv(p, w, c0, ldc, prb, nb);
     for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
       const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
-      { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb), p->half_y); }
-      { Timed t(p, st, CPB_K_Z_RHO); p->kz->z_rho(st, p->T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
+      { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
+      // rho is read-modify-written batch after batch: keep the order of the single-stream run
+      if (b > 0 && p->nws > 1) rt::stream_wait(w.s, p->ws[(b - 1) % p->nws].ev_rho);
+      { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, w.T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
+      rt::event_record(w.ev_rho, w.s);
     }
-    if (hooks) hooks->after_batch(b, off, nb);
+    if (hooks) hooks->after_batch(b, off, nb, w.s);
   }
+  join_streams(p, st, nbatches);
   rt::check_last("rhoofr kernels");
 }
 
 void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, const double* vpot,
               bool accumulate, cudaStream_t st, BatchHooks* hooks) {
+  const int nbatches = (np + p->max_batch - 1) / p->max_batch;
+  fork_streams(p, st, nbatches);
   int b = 0;
   for (int off = 0; off < np; off += p->max_batch, ++b) {
     const int nb = std::min(p->max_batch, np - off);
-    if (hooks) hooks->before_batch(b, off, nb);
+    cpb_plan::WorkSpace& w = p->ws[b % p->nws];
+    if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
-    run_x_inv(p, c0, ldc, prb, nb, st);
+    run_x_inv(p, w, c0, ldc, prb, nb);
     for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
       const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
-      const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb);
-      { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, p->T1, p->T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
-      { Timed t(p, st, CPB_K_Z_VPSI); p->kz->z_vpsi(st, p->T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1]), p->half_z); }
-      { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, p->T2, p->T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm);
+      { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, w.T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
+      { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, w.T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
     }
-    run_x_fwd(p, c0, c2, ldc, prb, nb, accumulate, st);
-    if (hooks) hooks->after_batch(b, off, nb);
+    run_x_fwd(p, w, c0, c2, ldc, prb, nb, accumulate);
+    if (hooks) hooks->after_batch(b, off, nb, w.s);
   }
+  join_streams(p, st, nbatches);
   rt::check_last("vpsi kernels");
 }
 
@@ -700,15 +738,23 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
-    p->T1 = (cplx*)rt::dmalloc(t1);
-    p->T2 = (cplx*)rt::dmalloc(t2);
-    p->G = (cplx*)rt::dmalloc(gb);
-    // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite.
-    rt::dzero(p->T1, t1, 0);
-    rt::dzero(p->T2, t2, 0);
-    rt::dzero(p->G, gb, 0);
+    if (const char* e = std::getenv("CPB_STREAMS")) p->nws = std::max(1, std::min((int)cpb_plan::kNumWS, std::atoi(e)));
+    for (int i = 0; i < p->nws; ++i) {
+      cpb_plan::WorkSpace& w = p->ws[i];
+      w.T1 = (cplx*)rt::dmalloc(t1);
+      w.T2 = (cplx*)rt::dmalloc(t2);
+      w.G = (cplx*)rt::dmalloc(gb);
+      // pad columns (x >= n1 in the last x tile) are never written by the x pass: keep them finite.
+      rt::dzero(w.T1, t1, 0);
+      rt::dzero(w.T2, t2, 0);
+      rt::dzero(w.G, gb, 0);
+      w.s = rt::stream_create();
+      w.ev_join = rt::event_create();
+      w.ev_rho = rt::event_create();
+    }
+    p->ev_fork = rt::event_create();
     rt::sync(0);
-    p->workspace_bytes = t1 + t2 + gb;
+    p->workspace_bytes = (size_t)p->nws * (t1 + t2 + gb);
     p->s_main = rt::stream_create();
     p->s_in = rt::stream_create();
     p->s_out = rt::stream_create();
@@ -785,6 +831,7 @@ int cpb_plan_get_info(const cpb_plan* p, cpb_plan_info* info) {
   info->band_pruned[1] = p->half_y;
   info->band_pruned[2] = p->half_z;
   info->chunk_xtiles = p->chunk_xt;
+  info->streams = p->nws;
   return CPB_OK;
 }
 
@@ -796,6 +843,15 @@ int cpb_plan_get_maps(const cpb_plan* p, int32_t* nzhs, int32_t* indzs) {
 }
 
 long cpb_plan_launch_count(const cpb_plan* p) { return p ? p->launches : 0; }
+
+int cpb_plan_set_streams(cpb_plan* p, int n) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  int have = 0;
+  for (const auto& w : p->ws) have += (w.T1 != nullptr);
+  if (n < 1 || n > have) return fail(CPB_ERR_INVALID, "stream count outside 1..allocated work spaces");
+  p->nws = n;
+  return CPB_OK;
+}
 
 int cpb_plan_set_profiling(cpb_plan* p, int on) {
   if (!p) return fail(CPB_ERR_INVALID, "null plan");

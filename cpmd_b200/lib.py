@@ -41,6 +41,7 @@ class PlanInfo(C.Structure):
         ("workspace_bytes", C.c_size_t),
         ("band_pruned", C.c_int * 3),
         ("chunk_xtiles", C.c_int),
+        ("streams", C.c_int),
     ]
 
 
@@ -70,6 +71,7 @@ SYMBOLS = {
                                C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
 }
 

@@ -80,6 +80,7 @@ typedef struct {
   size_t workspace_bytes;
   int band_pruned[3]; /* 1: the axis runs the band-pruned kernel variants (coefficients in the middle half) */
   int chunk_xtiles;   /* x tiles (of 8 columns) per y/z chunk; the chunk's intermediate stays in L2 */
+  int streams;        /* work spaces / streams the batches of a call alternate between */
 } cpb_plan_info;
 
 const char* cpb_last_error(void);
@@ -155,6 +156,10 @@ enum {
   CPB_NKINDS = 9
 };
 int cpb_plan_set_profiling(cpb_plan* plan, int on);
+/* Batches of a call alternate between `n` work spaces/streams, 1 <= n <= the number allocated at
+ * plan creation (env CPB_STREAMS, default 1 = all kernels serialised on one stream; 2 overlaps the
+ * HBM-bound kernels of one batch with the FP64-bound z kernel of the other). */
+int cpb_plan_set_streams(cpb_plan* plan, int n);
 int cpb_plan_get_kernel_times(cpb_plan* plan, double* ms /*[CPB_NKINDS]*/, long* counts /*[CPB_NKINDS]*/,
                               int reset);
 

@@ -3,5 +3,5 @@
 m=$1; s=$2; bs=$3; shift 3
 for b in $bs; do for e in "$@"; do
   echo "== batch $b env $e"
-  env $e timeout 300 python tools/gpu_probe.py $m $s $b 3 2>&1 | tail -2
+  env $e timeout 300 python tools/gpu_probe.py $m $s $b 3 2>&1 | tail -3
 done; done
