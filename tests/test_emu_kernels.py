@@ -193,3 +193,26 @@ def test_context_mirrors_reference_signatures(emu_cdll):
     ctx.delta = -1.0
     with pytest.raises(StopGM):
         ctx.rhoofr(d["c0"], rhoe, psi, ns)
+
+
+def test_two_work_spaces(emu_cdll, monkeypatch):
+    """CPB_STREAMS=2: consecutive batches alternate between two work spaces / streams; results are
+    bit-identical to the single-stream run (rho is still accumulated batch after batch in order)."""
+    d = synthetic.make_inputs(20, 9, f_pattern="mixed")
+    p1 = _plan(d, emu_cdll, max_batch=2)
+    assert p1.info["streams"] == 1
+    monkeypatch.setenv("CPB_STREAMS", "2")
+    p2 = _plan(d, emu_cdll, max_batch=2)
+    assert p2.info["streams"] == 2
+    r1, *s1 = p1.rhoofr(d["c0"], d["f"])
+    r2, *s2 = p2.rhoofr(d["c0"], d["f"])
+    assert np.array_equal(r1, r2) and s1 == s2
+    a = 0.25 * d["c0"]
+    b = a.copy()
+    p1.vpsi(d["c0"], a, d["f"], d["vpot"])
+    p2.vpsi(d["c0"], b, d["f"], d["vpot"])
+    assert np.array_equal(a, b)
+    p2.set_streams(1)
+    assert p2.info["streams"] == 1
+    with pytest.raises(CpbError):
+        p1.set_streams(2)                  # only one work space was allocated

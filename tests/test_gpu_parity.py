@@ -189,3 +189,18 @@ def test_full_size_properties(dev):
     geo = orc.make_geometry(n)
     ref = staged.vpsi(geo, d["c0"][:2], np.zeros_like(d["c0"][:2]), f[:2], d["vpot"], 1.0)
     assert relmax(c2[:2].cpu().numpy(), ref) < RTOL
+
+
+def test_two_streams_bit_identical(dev, monkeypatch):
+    """CPB_STREAMS=2 (batches alternate between two work-space streams) against the default."""
+    n, ns = 48, 13
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    p1 = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
+    monkeypatch.setenv("CPB_STREAMS", "2")
+    p2 = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
+    assert p2.info["streams"] == 2
+    r1, s1, c1 = _dev_run(p1, d, dev)
+    r2, s2, c2 = _dev_run(p2, d, dev)
+    assert np.array_equal(r1, r2) and s1 == s2 and np.array_equal(c1, c2)
+    geo = orc.make_geometry(n)
+    assert relmax(r2, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
