@@ -180,6 +180,66 @@ class Plan:
         self._check(rc)
         return c2
 
+    # -- LSD (cntl%tlsd): rhoe / vpot are (2, nnr1) arrays = Fortran (nnr1, 2) ---------------------
+    def rhoofr_lsd(self, c0, f, nsup, rhoe=None, nstate=None, ngroups=1, my_group=0, flags=0):
+        """``cpb_rhoofr_lsd`` (host arrays).  Returns (rhoe, ekin, rsum_g, rsum_r, csums, csumsabs)."""
+        c0 = _as_host(c0, np.complex128)
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if rhoe is None:
+            rhoe = np.empty((2, self.nnr1), dtype=np.float64)
+        rh = _as_host(rhoe, np.float64)
+        if rh.size < 2 * self.nnr1:
+            raise ValueError("rhoe too small (needs two columns)")
+        out = [C.c_double() for _ in range(5)]
+        rc = self._L.cpb_rhoofr_lsd(self._h, c0.ctypes.data, ld, nstate, f.ctypes.data, int(nsup), ngroups, my_group,
+                                    rh.ctypes.data, *[C.byref(o) for o in out], flags)
+        self._check(rc)
+        return (rhoe, *[o.value for o in out])
+
+    def vpsi_lsd(self, c0, c2, f, nsup, vpot, nstate=None, ngroups=1, my_group=0, flags=0):
+        """``cpb_vpsi_lsd`` (host arrays); vpot is (2, nnr1): [alpha, beta]."""
+        c0 = _as_host(c0, np.complex128)
+        c2h = _as_host(c2, np.complex128)
+        if c2h.shape != c0.shape:
+            raise ValueError("c2 must have the shape of c0")
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        v = _as_host(vpot, np.float64)
+        if v.size < 2 * self.nnr1:
+            raise ValueError("vpot too small (needs two columns)")
+        rc = self._L.cpb_vpsi_lsd(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data, int(nsup),
+                                  v.ctypes.data, ngroups, my_group, flags)
+        self._check(rc)
+        return c2
+
+    def rhoofr_lsd_dev(self, c0, f, nsup, rhoe, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if rhoe.numel() < 2 * self.nnr1:
+            raise ValueError("rhoe too small (needs two columns)")
+        out = [C.c_double() for _ in range(5)]
+        rc = self._L.cpb_rhoofr_lsd_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, int(nsup), ngroups, my_group,
+                                        _ptr(rhoe), *[C.byref(o) for o in out], flags, _stream_ptr(stream))
+        self._check(rc)
+        return tuple(o.value for o in out)
+
+    def vpsi_lsd_dev(self, c0, c2, f, nsup, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if vpot.numel() < 2 * self.nnr1:
+            raise ValueError("vpot too small (needs two columns)")
+        rc = self._L.cpb_vpsi_lsd_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, int(nsup), _ptr(vpot),
+                                      ngroups, my_group, flags, _stream_ptr(stream))
+        self._check(rc)
+        return c2
+
+    def lsd_finish_dev(self, rhoe, stream=None):
+        """rhoofr_utils.mod.F90:543-559 on group-summed channel densities; returns (rsum_r, csums, csumsabs)."""
+        out = [C.c_double() for _ in range(3)]
+        self._check(self._L.cpb_lsd_finish_dev(self._h, _ptr(rhoe), *[C.byref(o) for o in out], _stream_ptr(stream)))
+        return tuple(o.value for o in out)
+
     def c0_upload(self, c0, nstate=None, ngroups=1, my_group=0):
         c0 = _as_host(c0, np.complex128)
         nstate, ld = self._c0_args(c0, nstate)
@@ -268,6 +328,7 @@ class CpmdContext:
     ttau: bool = False                # cntl%ttau
     tdg: bool = False                 # tdgcomm%tdg
     rsactive: bool = False
+    nsup: int = 0                     # spin_mod%nsup (number of alpha states, used with tlsd)
     tksham: bool = False              # cntl%tksham
     akin: float = 0.0                 # prcp_com%akin
     nogrp: int = 1                    # group%nogrp (old task groups)
@@ -278,6 +339,8 @@ class CpmdContext:
     ekin: float = 0.0                 # ener_com%ekin
     csumg: float = 0.0                # chrg%csumg
     csumr: float = 0.0                # chrg%csumr
+    csums: float = 0.0                # chrg%csums    (LSD)
+    csumsabs: float = 0.0             # chrg%csumsabs (LSD)
 
     def __post_init__(self):
         if self.plan is None:
@@ -290,7 +353,7 @@ class CpmdContext:
     def _check_variant(self, proc):
         if self.nogrp > 1:
             raise StopGM(proc, "OLD TASK GROUPS NOT SUPPORTED ANYMORE ")  # vpsi_utils.mod.F90:173-175
-        for flag, name in ((self.tkpnt, "k-points"), (self.tlsd, "LSD"), (self.tlse, "LSE"),
+        for flag, name in ((self.tkpnt, "k-points"), (self.tlse, "LSE"),
                            (self.ttau, "meta-GGA tau"), (self.tdg, "double grid"),
                            (self.rsactive, "REAL SPACE WFN KEEP"), (self.akin > 1.0e-10, "AKIN")):
             if flag:
@@ -308,7 +371,16 @@ class CpmdContext:
             raise StopGM(proc, "occupation numbers crge%f not set")
         dev = _is_torch(c0) and c0.is_cuda
         rh = rhoe if rhoe.ndim == 1 else rhoe.reshape(-1)
-        if dev:
+        if self.tlsd:
+            # rhoe(nnr1, nlsd=2): a (2, nnr1) array here
+            if dev:
+                ekin, rg, rr, cs, ca = self.plan.rhoofr_lsd_dev(c0, self.f, self.nsup, rh, nstate, self.cp_nogrp,
+                                                                self.cp_inter_me)
+            else:
+                _, ekin, rg, rr, cs, ca = self.plan.rhoofr_lsd(c0, self.f, self.nsup, rh, nstate, self.cp_nogrp,
+                                                               self.cp_inter_me)
+            self.csums, self.csumsabs = cs, ca
+        elif dev:
             ekin, rg, rr = self.plan.rhoofr_dev(c0, self.f, rh, nstate, self.cp_nogrp, self.cp_inter_me)
         else:
             _, ekin, rg, rr = self.plan.rhoofr(c0, self.f, rh, nstate, self.cp_nogrp, self.cp_inter_me)
@@ -324,10 +396,16 @@ class CpmdContext:
         self._check_variant(proc)
         if ikind != 1:
             raise StopGM(proc, "k-points (ikind>1) not implemented on the GPU path")
-        if ispin != 1:
-            raise StopGM(proc, "LSD (ispin=2) not implemented on the GPU path")
         flags = _lib.CPB_VPSI_TKSHAM if self.tksham else 0
         v = vpot if vpot.ndim == 1 else vpot.reshape(-1)
+        if self.tlsd and ispin == 2:       # vpsi_utils.mod.F90:450: cntl%tlsd .AND. ispin == 2
+            if _is_torch(c0) and c0.is_cuda:
+                self.plan.vpsi_lsd_dev(c0, c2, f, self.nsup, v, nstate, self.cp_nogrp, self.cp_inter_me, flags)
+            else:
+                self.plan.vpsi_lsd(c0, c2, f, self.nsup, v, nstate, self.cp_nogrp, self.cp_inter_me, flags)
+            return
+        if ispin != 1:
+            raise StopGM(proc, "ispin=2 without cntl%tlsd")
         if _is_torch(c0) and c0.is_cuda:
             self.plan.vpsi_dev(c0, c2, f, v, nstate, self.cp_nogrp, self.cp_inter_me, flags)
         else:

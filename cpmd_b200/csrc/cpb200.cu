@@ -34,7 +34,8 @@ T* upload(const std::vector<T>& h) {
 }
 
 struct PairHost {
-  int s1, s2;  // 0-based global state indices, s2 = -1 for a trailing single state
+  int s1, s2;    // 0-based global state indices, s2 = -1 for a single-state transform
+  int chan = 0;  // LSD: spin channel (0 alpha, 1 beta) of the pair's real-space arrays
 };
 
 // part_1d.mod.F90:22-57
@@ -50,17 +51,40 @@ int get_el_in_blk(int i_elem, int n_elem, int proc, int nproc) {
   return i_elem + nbr * proc + std::min(proc, res);
 }
 
-// pairs formed inside the group's block: vpsi_utils.mod.F90:376-383, rhoofr_utils.mod.F90:306-310
-std::vector<PairHost> block_pairs(int nstate, int my_group, int ngroups) {
+// pairs formed inside the group's block: vpsi_utils.mod.F90:376-383, rhoofr_utils.mod.F90:306-310.
+// nsup >= 0 selects LSD (cntl%tlsd): states [0, nsup) are alpha, the rest beta (spin_mod%nsup).
+// The reference sends the Re part of a pair to the channel of is1 and the Im part to that of is2
+// (rhoofr_utils.mod.F90:375-385, vpsi_utils.mod.F90:450-482).  Here every launch works on one
+// channel, so the one pair that straddles the spin boundary (is1 == nsup, 1-based) is transformed
+// as two single states - the same linear map, the packing of two states into one transform being
+// an optimisation, not part of the result - and all alpha pairs precede all beta pairs.
+std::vector<PairHost> block_pairs(int nstate, int my_group, int ngroups, int nsup = -1) {
   std::vector<PairHost> out;
   const int nblk = nbr_el_in_blk(nstate, my_group, ngroups);
   for (int i = 1; i <= nblk; i += 2) {
     PairHost p;
     p.s1 = get_el_in_blk(i, nstate, my_group, ngroups) - 1;
     p.s2 = (i + 1 <= nblk) ? get_el_in_blk(i + 1, nstate, my_group, ngroups) - 1 : -1;
-    out.push_back(p);
+    p.chan = (nsup >= 0 && p.s1 >= nsup) ? 1 : 0;
+    if (nsup >= 0 && p.s2 >= 0 && p.s1 < nsup && p.s2 >= nsup) {
+      PairHost q;
+      q.s1 = p.s2;
+      q.s2 = -1;
+      q.chan = 1;
+      p.s2 = -1;
+      out.push_back(p);
+      out.push_back(q);
+    } else {
+      out.push_back(p);
+    }
   }
   return out;
+}
+// number of leading pairs that belong to channel 0
+int count_chan0(const std::vector<PairHost>& pairs) {
+  int n = 0;
+  while (n < (int)pairs.size() && pairs[n].chan == 0) ++n;
+  return n;
 }
 }  // namespace
 
@@ -74,6 +98,7 @@ struct cpb_plan {
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
+  double prologue_pairs = 0.5;  // block prologue cost in pair-times (pairs_per_group model)
   int x_sub = 16;         // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
@@ -116,7 +141,8 @@ struct cpb_plan {
   size_t d_c0_cap = 0;
   cplx* d_c2 = nullptr;
   size_t d_c2_cap = 0;
-  double* d_real = nullptr;  // rho or V, nnr1
+  double* d_real = nullptr;  // rho or V, d_real_cols * nnr1 (2 columns with LSD)
+  int d_real_cols = 0;
   cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
   std::vector<rt::event_t> ev_in, ev_done;
   // c0 cache key
@@ -316,8 +342,8 @@ void resolve_spans(cpb_plan* p) {
 // ceil(blocks / slots) waves, each lasting (pairs per block + block prologue) pair-times: pick the
 // group count that minimises that product.  Longer loops amortise the prologue and keep the
 // prefetch pipeline full; more groups cut the cost of the last, partially filled wave.
-int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group, int blocks_per_sm,
-                    double prologue = 0.5) {
+int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group, int blocks_per_sm) {
+  const double prologue = p->prologue_pairs;
   const long slots = (long)p->n_sm * std::max(blocks_per_sm, 1);
   int best = npair;
   double best_cost = 1e300;
@@ -404,13 +430,26 @@ void join_streams(cpb_plan* p, cudaStream_t st, int nbatches) {
 // `pr`: the call's pair descriptors, already uploaded (upload_pairs) - the host-pointer entry points
 // do that BEFORE they enqueue their bulk H2D copies, because the copy engine serves all streams in
 // FIFO order and the first kernel would otherwise wait behind the whole upload.
-void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, double* rho,
+// batches never straddle the channel boundary: [0, n0) work on channel 0, [n0, np) on channel 1
+struct BatchSpan {
+  int off, n, chan;
+};
+std::vector<BatchSpan> make_batches(const cpb_plan* p, int np, int n0) {
+  std::vector<BatchSpan> out;
+  for (int off = 0; off < n0; off += p->max_batch) out.push_back({off, std::min(p->max_batch, n0 - off), 0});
+  for (int off = n0; off < np; off += p->max_batch) out.push_back({off, std::min(p->max_batch, np - off), 1});
+  return out;
+}
+
+// rho0 / rho1: the density arrays of channel 0 / 1 (no LSD: n0 == np, rho1 unused)
+void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, int n0, double* rho0, double* rho1,
                 cudaStream_t st, BatchHooks* hooks) {
-  const int nbatches = (np + p->max_batch - 1) / p->max_batch;
+  const std::vector<BatchSpan> batches = make_batches(p, np, n0);
+  const int nbatches = (int)batches.size();
   fork_streams(p, st, nbatches);
-  int b = 0;
-  for (int off = 0; off < np; off += p->max_batch, ++b) {
-    const int nb = std::min(p->max_batch, np - off);
+  for (int b = 0; b < nbatches; ++b) {
+    const int off = batches[b].off, nb = batches[b].n;
+    double* rho = batches[b].chan ? rho1 : rho0;
     cpb_plan::WorkSpace& w = p->ws[b % p->nws];
     if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
@@ -429,13 +468,15 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
   rt::check_last("rhoofr kernels");
 }
 
-void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, const double* vpot,
-              bool accumulate, cudaStream_t st, BatchHooks* hooks) {
-  const int nbatches = (np + p->max_batch - 1) / p->max_batch;
+// v0 / v1: the potentials of channel 0 / 1 (no LSD: n0 == np, v1 unused)
+void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, int n0, const double* v0,
+              const double* v1, bool accumulate, cudaStream_t st, BatchHooks* hooks) {
+  const std::vector<BatchSpan> batches = make_batches(p, np, n0);
+  const int nbatches = (int)batches.size();
   fork_streams(p, st, nbatches);
-  int b = 0;
-  for (int off = 0; off < np; off += p->max_batch, ++b) {
-    const int nb = std::min(p->max_batch, np - off);
+  for (int b = 0; b < nbatches; ++b) {
+    const int off = batches[b].off, nb = batches[b].n;
+    const double* vpot = batches[b].chan ? v1 : v0;
     cpb_plan::WorkSpace& w = p->ws[b % p->nws];
     if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
@@ -469,6 +510,13 @@ void launch_sum(cpb_plan* p, const double* a, size_t n, double* out, cudaStream_
   CPB_LAUNCH(k, dim3(kSumBlocks), dim3(256), 256 * sizeof(double), st, a, n, out);
 }
 
+// LSD: partial sums of alpha, beta and |alpha - beta| -> out[3 * kSumBlocks]; finalize: alpha += beta
+void launch_lsd_sums(cpb_plan* p, double* a, const double* b, size_t n, double* out, bool finalize, cudaStream_t st) {
+  auto k = k_lsd_sums;
+  Timed t(p, st, CPB_K_SUM);
+  CPB_LAUNCH(k, dim3(kSumBlocks), dim3(256), 3 * 256 * sizeof(double), st, a, b, n, out, finalize ? 1 : 0);
+}
+
 void vpsi_coefs(const std::vector<PairHost>& pairs, const double* f, bool tksham, std::vector<double>& fi,
                 std::vector<double>& fip1) {
   // vpsi_utils.mod.F90:627-633
@@ -498,9 +546,10 @@ void rho_coefs(cpb_plan* p, const std::vector<PairHost>& all, const double* f, s
   }
 }
 
-// finish rhoofr: scalars from d_red (layout: [kRedPerState*count kin/dotp partials][kSumBlocks rho partials])
-void finish_rho_scalars(cpb_plan* p, const double* f, int first, int count, double* ekin, double* rsum_g,
-                        double* rsum_r) {
+// finish rhoofr: scalars from d_red (layout: [kRedPerState*count kin/dotp partials][rho partials:
+// kSumBlocks sums, or with LSD 3*kSumBlocks: alpha, beta, |alpha-beta|])
+void finish_rho_scalars(cpb_plan* p, const double* f, int first, int count, bool lsd, double* ekin, double* rsum_g,
+                        double* rsum_r, double* csums, double* csumsabs) {
   double xkin = 0.0, rsum = 0.0;
   for (int i = 0; i < count; ++i) {
     const double fi = f[first + i];
@@ -514,11 +563,19 @@ void finish_rho_scalars(cpb_plan* p, const double* f, int first, int count, doub
       xkin += fi * sk;
     }
   }
-  double s = 0.0;
-  for (int i = 0; i < kSumBlocks; ++i) s += p->h_red[(size_t)kRedPerState * count + i];
+  const double* hs = p->h_red + (size_t)kRedPerState * count;
+  const double w = p->omega / ((double)p->nr[0] * p->nr[1] * p->nr[2]);
+  double sa = 0.0, sb = 0.0, sabs = 0.0;
+  for (int i = 0; i < kSumBlocks; ++i) sa += hs[i];
+  if (lsd) {
+    for (int i = 0; i < kSumBlocks; ++i) sb += hs[kSumBlocks + i];
+    for (int i = 0; i < kSumBlocks; ++i) sabs += hs[2 * kSumBlocks + i];
+  }
   if (ekin) *ekin = xkin * p->tpiba2;
   if (rsum_g) *rsum_g = rsum;
-  if (rsum_r) *rsum_r = s * p->omega / ((double)p->nr[0] * p->nr[1] * p->nr[2]);
+  if (rsum_r) *rsum_r = (sa + sb) * w;           // rhoofr_utils.mod.F90:607-619 (column 1 = alpha + beta)
+  if (csums) *csums = lsd ? (sa - sb) * w : 0.0;  // :557
+  if (csumsabs) *csumsabs = lsd ? sabs * w : 0.0; // :558 (meaningful only on the group-summed density)
 }
 
 int check_common(cpb_plan* p, const void* c0, long ld, int nstate, const double* f, int ngroups,
@@ -733,6 +790,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     if (const char* e = std::getenv("CPB_CHUNK_XT")) p->chunk_xt = std::max(1, std::min(p->nxt, std::atoi(e)));
     p->t1_pair = (size_t)p->nxt * nrays * Bx;
     if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("CPB_PROLOGUE")) p->prologue_pairs = std::max(0.0, std::atof(e));
     p->x_sub = std::min(p->x_sub, p->max_batch);
     p->g_pair = (size_t)nxb * nrp;
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
@@ -875,11 +933,12 @@ int cpb_plan_get_kernel_times(cpb_plan* p, double* ms, long* counts, int reset) 
 // ---------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ---------------------------------------------------------------------------------------------
-int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, const double* f, int ngroups,
-                   int my_group, double* rhoe_dev, double* ekin, double* rsum_g, double* rsum_r,
-                   unsigned flags, void* stream) {
+static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, const double* f, int nsup,
+                           int ngroups, int my_group, double* rhoe_dev, double* ekin, double* rsum_g,
+                           double* rsum_r, double* csums, double* csumsabs, unsigned flags, void* stream) {
   if (int e = check_common(p, c0_dev, ld_c0, nstate, f, ngroups, my_group)) return e;
   if (!rhoe_dev) return fail(CPB_ERR_INVALID, "null rhoe");
+  if (nsup > nstate) return fail(CPB_ERR_INVALID, "nsup larger than nstate");
   try {
     rt::set_device(p->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -888,17 +947,22 @@ int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, cons
     const int first = nblk > 0 ? get_el_in_blk(1, nstate, my_group, ngroups) - 1 : 0;
     std::vector<PairHost> pairs;
     std::vector<double> ca, cb;
-    rho_coefs(p, block_pairs(nstate, my_group, ngroups), f, pairs, ca, cb);
-    ensure_red(p, kRedPerState * nblk + kSumBlocks);
-    rt::dzero(rhoe_dev, p->nnr1() * sizeof(double), st);  // rhoofr_utils.mod.F90:198
-    launch_kin(p, c0, ld_c0, first, nblk, st);               // :178
-    run_rhoofr(p, c0, ld_c0, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), rhoe_dev, st, nullptr);
-    launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + kRedPerState * nblk, st);  // :607-619
-    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + kSumBlocks) * sizeof(double), st);
+    const bool lsd = nsup >= 0;
+    const size_t nnr1 = p->nnr1();
+    rho_coefs(p, block_pairs(nstate, my_group, ngroups, nsup), f, pairs, ca, cb);
+    ensure_red(p, kRedPerState * nblk + 3 * kSumBlocks);
+    rt::dzero(rhoe_dev, (lsd ? 2 : 1) * nnr1 * sizeof(double), st);  // rhoofr_utils.mod.F90:198
+    launch_kin(p, c0, ld_c0, first, nblk, st);                        // :178
+    run_rhoofr(p, c0, ld_c0, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), count_chan0(pairs), rhoe_dev,
+               rhoe_dev + nnr1, st, nullptr);
+    double* d_sums = p->d_red + kRedPerState * nblk;
+    if (lsd) launch_lsd_sums(p, rhoe_dev, rhoe_dev + nnr1, nnr1, d_sums, ngroups == 1, st);  // :543-559
+    else launch_sum(p, rhoe_dev, nnr1, d_sums, st);                                            // :607-619
+    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + 3 * kSumBlocks) * sizeof(double), st);
     rt::sync(st);
     resolve_spans(p);
     double rg = 0, rr = 0;
-    finish_rho_scalars(p, f, first, nblk, ekin, &rg, &rr);
+    finish_rho_scalars(p, f, first, nblk, lsd, ekin, &rg, &rr, csums, csumsabs);
     if (rsum_g) *rsum_g = rg;
     if (rsum_r) *rsum_r = rr;
     if ((flags & CPB_RHO_CHECK_CHARGE) && ngroups == 1 && std::fabs(rr - rg) > 1.0e-6)
@@ -911,17 +975,52 @@ int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, cons
   }
 }
 
-int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
-                 const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
-  if (int e = check_common(p, c0_dev, ld, nstate, f, ngroups, my_group)) return e;
-  if (!c2_dev || !vpot_dev) return fail(CPB_ERR_INVALID, "null c2 or vpot");
+int cpb_rhoofr_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, const double* f, int ngroups,
+                   int my_group, double* rhoe_dev, double* ekin, double* rsum_g, double* rsum_r,
+                   unsigned flags, void* stream) {
+  return rhoofr_dev_impl(p, c0_dev, ld_c0, nstate, f, -1, ngroups, my_group, rhoe_dev, ekin, rsum_g, rsum_r, nullptr,
+                         nullptr, flags, stream);
+}
+
+int cpb_rhoofr_lsd_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, const double* f, int nsup,
+                       int ngroups, int my_group, double* rhoe_dev, double* ekin, double* rsum_g, double* rsum_r,
+                       double* csums, double* csumsabs, unsigned flags, void* stream) {
+  if (nsup < 0) return fail(CPB_ERR_INVALID, "negative nsup");
+  return rhoofr_dev_impl(p, c0_dev, ld_c0, nstate, f, nsup, ngroups, my_group, rhoe_dev, ekin, rsum_g, rsum_r, csums,
+                         csumsabs, flags, stream);
+}
+
+int cpb_lsd_finish_dev(cpb_plan* p, double* rhoe_dev, double* rsum_r, double* csums, double* csumsabs,
+                       void* stream) {
+  if (!p || !rhoe_dev) return fail(CPB_ERR_INVALID, "null argument");
   try {
     rt::set_device(p->device);
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups);
+    ensure_red(p, 3 * kSumBlocks);
+    launch_lsd_sums(p, rhoe_dev, rhoe_dev + p->nnr1(), p->nnr1(), p->d_red, true, st);
+    rt::d2h(p->h_red, p->d_red, (size_t)3 * kSumBlocks * sizeof(double), st);
+    rt::sync(st);
+    resolve_spans(p);
+    finish_rho_scalars(p, nullptr, 0, 0, true, nullptr, nullptr, rsum_r, csums, csumsabs);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
+}
+
+static int vpsi_dev_impl(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                         int nsup, const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
+  if (int e = check_common(p, c0_dev, ld, nstate, f, ngroups, my_group)) return e;
+  if (!c2_dev || !vpot_dev) return fail(CPB_ERR_INVALID, "null c2 or vpot");
+  if (nsup > nstate) return fail(CPB_ERR_INVALID, "nsup larger than nstate");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups, nsup);
     std::vector<double> fi, fip1;
     vpsi_coefs(pairs, f, (flags & CPB_VPSI_TKSHAM) != 0, fi, fip1);
-    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, fip1, st), (int)pairs.size(), vpot_dev,
+    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, fip1, st), (int)pairs.size(),
+             count_chan0(pairs), vpot_dev, vpot_dev + p->nnr1(),
              !(flags & CPB_VPSI_OVERWRITE), st, nullptr);
     rt::sync(st);
     resolve_spans(p);
@@ -931,6 +1030,17 @@ int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nst
   } catch (const std::bad_alloc&) {
     return fail(CPB_ERR_NOMEM, "out of host memory");
   }
+}
+
+int cpb_vpsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                 const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
+  return vpsi_dev_impl(p, c0_dev, c2_dev, ld, nstate, f, -1, vpot_dev, ngroups, my_group, flags, stream);
+}
+
+int cpb_vpsi_lsd_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f, int nsup,
+                     const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
+  if (nsup < 0) return fail(CPB_ERR_INVALID, "negative nsup");
+  return vpsi_dev_impl(p, c0_dev, c2_dev, ld, nstate, f, nsup, vpot_dev, ngroups, my_group, flags, stream);
 }
 
 }  // extern "C"

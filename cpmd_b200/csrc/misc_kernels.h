@@ -65,6 +65,39 @@ CPB_GLOBAL k_sum(const double* CPB_RESTRICT a, size_t n, double* CPB_RESTRICT pa
   if (tid == 0) partial[blockIdx.x] = red[0];
 }
 
+// LSD post-processing (rhoofr_utils.mod.F90:543-559): per-block partial sums of alpha, beta and
+// |alpha - beta| (fixed order); finalize != 0: column 1 becomes alpha + beta.  block = 256,
+// partial[0..g) alpha, [g..2g) beta, [2g..3g) |alpha - beta| with g = gridDim.x
+CPB_GLOBAL k_lsd_sums(double* a, const double* CPB_RESTRICT b, size_t n, double* CPB_RESTRICT partial, int finalize) {
+  CPB_DYN_SMEM(double, red);  // 3*256
+  const int tid = threadIdx.x;
+  double sa = 0.0, sb = 0.0, sd = 0.0;
+  for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256) {
+    const double x = a[i], y = b[i];
+    sa += x;
+    sb += y;
+    sd += (x - y < 0.0) ? (y - x) : (x - y);
+    if (finalize) a[i] = x + y;
+  }
+  red[tid] = sa;
+  red[256 + tid] = sb;
+  red[512 + tid] = sd;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (tid < k) {
+      red[tid] += red[tid + k];
+      red[256 + tid] += red[256 + tid + k];
+      red[512 + tid] += red[512 + tid + k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    partial[blockIdx.x] = red[0];
+    partial[gridDim.x + blockIdx.x] = red[256];
+    partial[2 * gridDim.x + blockIdx.x] = red[512];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_unpack: vpsi_utils.mod.F90:626-673 + add_wfn (:717).  Reads FFT[V psi] at +G and -G from the
 // band-ray storage G (kernels.h; already scaled by 1/N in k_x_fwd), separates the two states, adds the

@@ -62,6 +62,19 @@ SYMBOLS = {
                              C.POINTER(C.c_double), C.c_uint]),
     "cpb_vpsi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
                            C.c_int, C.c_int, C.c_uint]),
+    "cpb_rhoofr_lsd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint]),
+    "cpb_vpsi_lsd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "cpb_rhoofr_lsd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.c_uint, C.c_void_p]),
+    "cpb_vpsi_lsd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "cpb_lsd_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.c_void_p]),
     "cpb_c0_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int]),
     "cpb_c0_invalidate": (C.c_int, [C.c_void_p]),
     "cpb_rhoofr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int,

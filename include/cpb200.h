@@ -33,7 +33,7 @@
  * Layout conventions are the reference's: c0/c2 are column-major (ld, nstate) COMPLEX*16, one
  * column per state, ngw <= ld; rhoe/vpot are REAL*8 (kr1, kr2s, kr3s) x-fastest with the
  * odd-padded leading dimensions of leadim (loadpa_utils.mod.F90:509-525); inyh is INTEGER*4
- * (3,ngw), 1-based.  Only the supported variant is implemented: Gamma point, no LSD/LSE, no
+ * (3,ngw), 1-based.  Implemented variants: Gamma point, RKS and LSD; no LSE, no
  * tau, no double grid, akin = 0 — the shim must route everything else to the original routine
  * (list in INTEGRATION.md).
  */
@@ -115,6 +115,37 @@ int cpb_rhoofr(cpb_plan* plan, const void* c0, long ld_c0, int nstate, const dou
 
 int cpb_vpsi(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, const double* f,
              const double* vpot, int ngroups, int my_group, unsigned flags);
+
+/* ---- LSD (cntl%tlsd) variants --------------------------------------------------------------
+ * States 1..nsup are alpha, nsup+1..nstate beta (spin_mod%nsup).  rhoe and vpot have two columns,
+ * (nnr1, 2) column-major like the reference's rhoe(nnr1,nlsd) / vpot(nnr1,ispin):
+ *   cpb_rhoofr_lsd  rhoofr with cntl%tlsd (rhoofr_utils.mod.F90:375-385, 543-559).  ngroups == 1:
+ *                   on return column 1 = alpha+beta density, column 2 = beta density, csums =
+ *                   integral of alpha-beta, csumsabs = integral of |alpha-beta| (chrg%csums,
+ *                   chrg%csumsabs).  ngroups > 1: the columns hold the group's partial alpha and
+ *                   beta densities - the reference applies cp_grp_redist(rhoe,nnr1,nlsd) (:457-461)
+ *                   before that step - rsum_r / csums are the group's partial sums and csumsabs is
+ *                   not meaningful; finish with the original lines :543-559 or cpb_lsd_finish_dev.
+ *   cpb_vpsi_lsd    vpsi with cntl%tlsd and ispin = 2 (vpsi_utils.mod.F90:450-482): column 1 of vpot
+ *                   acts on the alpha states, column 2 on the beta states.
+ * Every launch works on one spin channel; the one pair that straddles the spin boundary is
+ * transformed as two single states (the same linear map as the reference's mixed pair). */
+int cpb_rhoofr_lsd(cpb_plan* plan, const void* c0, long ld_c0, int nstate, const double* f, int nsup,
+                   int ngroups, int my_group, double* rhoe, double* ekin, double* rsum_g,
+                   double* rsum_r, double* csums, double* csumsabs, unsigned flags);
+int cpb_vpsi_lsd(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, const double* f,
+                 int nsup, const double* vpot, int ngroups, int my_group, unsigned flags);
+int cpb_rhoofr_lsd_dev(cpb_plan* plan, const void* c0_dev, long ld_c0, int nstate, const double* f,
+                       int nsup, int ngroups, int my_group, double* rhoe_dev, double* ekin,
+                       double* rsum_g, double* rsum_r, double* csums, double* csumsabs,
+                       unsigned flags, void* stream);
+int cpb_vpsi_lsd_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate,
+                     const double* f, int nsup, const double* vpot_dev, int ngroups, int my_group,
+                     unsigned flags, void* stream);
+/* rhoofr_utils.mod.F90:543-559 on the group-summed channel densities (device array (nnr1,2)):
+ * column 1 += column 2, and the three integrals. */
+int cpb_lsd_finish_dev(cpb_plan* plan, double* rhoe_dev, double* rsum_r, double* csums,
+                       double* csumsabs, void* stream);
 
 /* Optional: keep the group's block of c0 on the device between rhoofr and the following vpsi of
  * the same MD step (the reference's cp_cuwfn cache, vpsi_utils.mod.F90:268-273, which trusts a

@@ -358,6 +358,89 @@ def vpsi(geo: Geometry, c0, c2, f, vpot, tpiba2, group=0, ngroups=1, redist_c2=F
     return c2 + c2v                                                   # :717
 
 
+# ----------------------------------------------------------------------------------------------
+# LSD (cntl%tlsd) variants: states 1..nsup are alpha, nsup+1..nstate beta (spin_mod%nsup)
+# ----------------------------------------------------------------------------------------------
+
+def lsd_finish(geo: Geometry, rhoe2, omega):
+    """rhoofr_utils.mod.F90:543-559 + :607-619, applied to the two channel densities *after* the
+    group sum (cp_grp_redist, :457-461): csums / csumsabs from alpha - beta, then column 1 becomes
+    alpha + beta; column 2 stays beta.  rhoe2: (2, nnr1), modified in place.
+    Returns (rsum_r, csums, csumsabs)."""
+    n1, n2, n3 = geo.nr
+    w = omega / float(n1 * n2 * n3)
+    d = rhoe2[0] - rhoe2[1]
+    csums = float(np.sum(d)) * w
+    csumsabs = float(np.sum(np.abs(d))) * w
+    rhoe2[0] += rhoe2[1]
+    return float(np.sum(rhoe2[0])) * w, csums, csumsabs
+
+
+def rhoofr_lsd(geo: Geometry, c0, f, omega, tpiba2, nsup, group=0, ngroups=1):
+    """``rhoofr`` with cntl%tlsd (rhoofr_utils.mod.F90:375-385): the Re part of a pair goes to the
+    spin channel of is1, the Im part to that of is2 (a missing partner counts as is2 = nstate+1,
+    :308, i.e. beta, with coef4 = 0).  Returns dict(rhoe (2, nnr1), ekin, rsum_g, rsum_r, csums,
+    csumsabs): for ngroups == 1 rhoe[0] = alpha+beta, rhoe[1] = beta (:543-559); for ngroups > 1
+    the group's *partial* alpha and beta densities (the reference sums over groups first; finish
+    with :func:`lsd_finish`), and rsum_r/csums/csumsabs are None."""
+    nstate = c0.shape[0]
+    ekin, rsum = kin_energy(geo, c0, f, tpiba2)
+    rhoe = np.zeros((2, geo.nnr1), dtype=np.float64)
+    for is1, is2 in state_pairs(nstate, group, ngroups):
+        tfcal = f[is1] != 0.0 or (is2 is not None and f[is2] != 0.0)
+        if not tfcal:
+            continue
+        psi = set_psi_1_state_g(geo, c0[is1]) if is2 is None else set_psi_2_states_g(geo, c0[is1], c0[is2])
+        psi = invfftn_sparse(geo, psi)
+        coef3 = f[is1] / omega
+        coef4 = 0.0 if is2 is None else f[is2] / omega
+        ispin1 = 1 if (is1 + 1) > nsup else 0                         # :378 (1-based is1)
+        ispin2 = 1 if ((nstate + 1) if is2 is None else (is2 + 1)) > nsup else 0   # :379
+        if ispin1 == ispin2:
+            rhoe[ispin1] += coef3 * psi.real ** 2 + coef4 * psi.imag ** 2      # :381
+        else:
+            rhoe[ispin1] += coef3 * psi.real ** 2                              # :383
+            rhoe[ispin2] += coef4 * psi.imag ** 2                              # :384
+    out = dict(rhoe=rhoe, ekin=ekin, rsum_g=rsum, rsum_r=None, csums=None, csumsabs=None)
+    if ngroups == 1:
+        out["rsum_r"], out["csums"], out["csumsabs"] = lsd_finish(geo, rhoe, omega)
+    return out
+
+
+def vpsi_lsd(geo: Geometry, c0, c2, f, vpot2, tpiba2, nsup, group=0, ngroups=1, tksham=False):
+    """``vpsi`` with cntl%tlsd and ispin = 2 (vpsi_utils.mod.F90:450-482): vpot2 is (2, nnr1)
+    [alpha, beta]; the pair that straddles the spin boundary (is1 == nsup, 1-based) gets
+    V_alpha * Re(psi) + i V_beta * Im(psi), every other pair the potential of is1's spin."""
+    nstate = c0.shape[0]
+    c2v = np.zeros_like(c2)
+    for is1, is2 in state_pairs(nstate, group, ngroups):
+        psi = set_psi_1_state_g(geo, c0[is1]) if is2 is None else set_psi_2_states_g(geo, c0[is1], c0[is2])
+        psi = invfftn_sparse(geo, psi)
+        if is1 + 1 == nsup:                                                    # :451
+            psi = vpot2[0] * psi.real + 1j * vpot2[1] * psi.imag               # :466-469
+        else:
+            lspin = 1 if (is1 + 1) > nsup else 0                               # :475-476
+            psi = vpot2[lspin] * psi                                           # :481
+        psi = fwfftn_sparse(geo, psi)
+        fi = f[is1] * 0.5
+        if fi == 0.0:
+            fi = 0.5 if tksham else 1.0
+        fip1 = 0.0
+        if is2 is not None:
+            fip1 = f[is2] * 0.5
+        if fip1 == 0.0:
+            fip1 = 0.5 if tksham else 1.0
+        psin = psi[geo.nzhs - 1]
+        psii = psi[geo.indzs - 1]
+        fp = psin + psii
+        fm = psin - psii
+        g2 = tpiba2 * geo.hg
+        c2v[is1] = -fi * (g2 * c0[is1] + (fp.real + 1j * fm.imag))
+        if is2 is not None:
+            c2v[is2] = -fip1 * (g2 * c0[is2] + (fp.imag - 1j * fm.real))
+    return c2 + c2v
+
+
 def e_test(geo: Geometry, rho_out, vpot, omega):
     """The synthetic "total energy" used for the 1e-9 Ha criterion:
     E_test = ekin + (Omega/N) * sum_r V(r) rho(r)."""

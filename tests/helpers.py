@@ -28,3 +28,17 @@ def load_golden(path):
         d[k] = int(d[k])
     d["nr"] = tuple(int(v) for v in d["nr"])
     return d
+
+
+def golden_lsd_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "lsd", "*.npz")))
+
+
+def load_golden_lsd(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    for k in ("omega", "tpiba2", "ekin", "rsum_g", "rsum_r", "csums", "csumsabs"):
+        d[k] = float(d[k])
+    d["nsup"] = int(d["nsup"])
+    d["nr"] = tuple(int(v) for v in d["nr"])
+    return d

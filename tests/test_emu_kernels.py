@@ -184,10 +184,10 @@ def test_context_mirrors_reference_signatures(emu_cdll):
     # unsupported variants stop like the reference
     with pytest.raises(StopGM):
         ctx.vpsi(d["c0"], c2, d["f"], d["vpot"], psi, ns, ikind=2)
-    ctx.tlsd = True
+    ctx.tlse = True
     with pytest.raises(StopGM):
         ctx.rhoofr(d["c0"], rhoe, psi, ns)
-    ctx.tlsd = False
+    ctx.tlse = False
     # charge check (rhoofr_utils.mod.F90:625-635): a non-normalisable input still passes the
     # identity, so provoke it by lying about omega-independent sums via delta
     ctx.delta = -1.0
@@ -216,3 +216,56 @@ def test_two_work_spaces(emu_cdll, monkeypatch):
     assert p2.info["streams"] == 1
     with pytest.raises(CpbError):
         p1.set_streams(2)                  # only one work space was allocated
+
+
+@pytest.mark.parametrize("n,nstate,nsup,mb", [(16, 7, 3, 2), (16, 7, 4, 2), (20, 6, 0, 16), (20, 6, 6, 16),
+                                              (24, 9, 5, 1), (16, 2, 1, 16)])
+def test_lsd_matches_oracle(emu_cdll, n, nstate, nsup, mb):
+    """cntl%tlsd: rhoofr_utils.mod.F90:375-385,543-559 and vpsi_utils.mod.F90:450-482."""
+    d = synthetic.make_inputs(n, nstate, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    p = _plan(d, emu_cdll, max_batch=mb)
+    ref = orc.rhoofr_lsd(geo, d["c0"], d["f"], 1.0, 1.0, nsup)
+    rho, ekin, rg, rr, cs, ca = p.rhoofr_lsd(d["c0"], d["f"], nsup)
+    scale = np.abs(ref["rhoe"][0]).max()
+    assert np.abs(rho - ref["rhoe"]).max() / scale < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL and abs(rg - ref["rsum_g"]) < ETOL and abs(rr - ref["rsum_r"]) < ETOL
+    assert abs(cs - ref["csums"]) < ETOL and abs(ca - ref["csumsabs"]) < ETOL
+    v2 = np.stack([d["vpot"], 0.5 * d["vpot"][::-1]])
+    c2 = 0.5 * d["c0"]
+    c2_ref = orc.vpsi_lsd(geo, d["c0"], c2, d["f"], v2, 1.0, nsup)
+    p.vpsi_lsd(d["c0"], c2, d["f"], nsup, v2)
+    assert relmax(c2, c2_ref) < RTOL
+
+
+def test_lsd_groups_and_context(emu_cdll):
+    n, ns, nsup = 16, 9, 4
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    p = _plan(d, emu_cdll, max_batch=2)
+    v2 = np.stack([d["vpot"], 0.25 * d["vpot"]])
+    full = orc.rhoofr_lsd(geo, d["c0"], d["f"], 1.0, 1.0, nsup)
+    c2_full = orc.vpsi_lsd(geo, d["c0"], np.zeros_like(d["c0"]), d["f"], v2, 1.0, nsup)
+    acc = np.zeros((2, p.nnr1))
+    c2 = np.zeros_like(d["c0"])
+    for grp in range(3):
+        rho, *_ = p.rhoofr_lsd(d["c0"], d["f"], nsup, ngroups=3, my_group=grp)
+        part = orc.rhoofr_lsd(geo, d["c0"], d["f"], 1.0, 1.0, nsup, group=grp, ngroups=3)["rhoe"]
+        assert np.abs(rho - part).max() < RTOL * np.abs(full["rhoe"][0]).max()    # raw partial channels
+        acc += rho
+        p.vpsi_lsd(d["c0"], c2, d["f"], nsup, v2, ngroups=3, my_group=grp)
+    rr, cs, ca = orc.lsd_finish(geo, acc, 1.0)                                   # after cp_grp_redist
+    assert np.abs(acc - full["rhoe"]).max() < RTOL * np.abs(full["rhoe"][0]).max()
+    assert abs(cs - full["csums"]) < ETOL and abs(ca - full["csumsabs"]) < ETOL and abs(rr - full["rsum_r"]) < ETOL
+    assert relmax(c2, c2_full) < RTOL
+    # the context with cntl%tlsd mirrors rhoe(nnr1,2) / vpot(nnr1,2)
+    ctx = CpmdContext(nr=d["nr"], inyh=d["inyh"], hg=d["hg"], f=d["f"], tlsd=True, nsup=nsup, _cdll=emu_cdll)
+    rhoe = np.zeros((2, ctx.nnr1))
+    ctx.rhoofr(d["c0"], rhoe, None, ns)
+    assert np.abs(rhoe - full["rhoe"]).max() < RTOL * np.abs(full["rhoe"][0]).max()
+    assert abs(ctx.csums - full["csums"]) < ETOL and abs(ctx.csumsabs - full["csumsabs"]) < ETOL
+    c2b = np.zeros_like(d["c0"])
+    ctx.vpsi(d["c0"], c2b, d["f"], v2, None, ns, 1, 2, False)
+    assert relmax(c2b, c2_full) < RTOL
+    with pytest.raises(CpbError):
+        p.rhoofr_lsd(d["c0"], d["f"], ns + 1)

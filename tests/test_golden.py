@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import ETOL, RTOL, golden_cases, load_golden, relmax
+from helpers import ETOL, RTOL, golden_cases, golden_lsd_cases, load_golden, load_golden_lsd, relmax
 from oracle import cpmd_oracle as orc
 from oracle import staged
 
@@ -22,3 +22,20 @@ def test_oracles_reproduce_golden(path):
 
 def test_golden_present():
     assert len(golden_cases()) >= 4
+
+
+@pytest.mark.parametrize("path", golden_lsd_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_and_simulator_reproduce_lsd_golden(emu_cdll, path):
+    from cpmd_b200.api import Plan
+    d = load_golden_lsd(path)
+    geo = orc.fft_maps(d["nr"], d["inyh"], d["hg"])
+    r = orc.rhoofr_lsd(geo, d["c0"], d["f"], d["omega"], d["tpiba2"], d["nsup"])
+    assert np.array_equal(r["rhoe"], d["rhoe"]) and r["csums"] == d["csums"]
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2, _cdll=emu_cdll)
+    rho, ekin, rg, rr, cs, ca = p.rhoofr_lsd(d["c0"], d["f"], d["nsup"])
+    assert np.abs(rho - d["rhoe"]).max() < RTOL * np.abs(d["rhoe"][0]).max()
+    assert abs(ekin - d["ekin"]) < ETOL and abs(cs - d["csums"]) < ETOL and abs(ca - d["csumsabs"]) < ETOL
+    c2 = d["c2_in"].copy()
+    p.vpsi_lsd(d["c0"], c2, d["f"], d["nsup"], d["vpot"])
+    assert relmax(c2, d["c2_out"]) < RTOL
+    assert len(golden_lsd_cases()) >= 2

@@ -204,3 +204,39 @@ def test_two_streams_bit_identical(dev, monkeypatch):
     assert np.array_equal(r1, r2) and s1 == s2 and np.array_equal(c1, c2)
     geo = orc.make_geometry(n)
     assert relmax(r2, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+
+
+@pytest.mark.parametrize("n,nstate,nsup,mb", [(24, 7, 3, 2), (48, 10, 5, 2), (64, 6, 4, 16), (96, 5, 0, 2)])
+def test_lsd_device_and_host(dev, n, nstate, nsup, mb):
+    """cntl%tlsd through both entry-point families against the oracle."""
+    d = synthetic.make_inputs(n, nstate, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=mb)
+    ref = orc.rhoofr_lsd(geo, d["c0"], d["f"], 1.0, 1.0, nsup)
+    scale = np.abs(ref["rhoe"][0]).max()
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    rho = torch.full((2, plan.nnr1), 3.0, dtype=torch.float64, device=dev)
+    ekin, rg, rr, cs, ca = plan.rhoofr_lsd_dev(c0, d["f"], nsup, rho)
+    assert np.abs(rho.cpu().numpy() - ref["rhoe"]).max() / scale < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"])) and abs(rr - ref["rsum_r"]) < ETOL
+    assert abs(cs - ref["csums"]) < ETOL and abs(ca - ref["csumsabs"]) < ETOL
+    v2 = np.stack([d["vpot"], 0.5 * d["vpot"][::-1]])
+    c2_ref = orc.vpsi_lsd(geo, d["c0"], 0.5 * d["c0"], d["f"], v2, 1.0, nsup)
+    c2 = 0.5 * c0
+    plan.vpsi_lsd_dev(c0, c2, d["f"], nsup, torch.from_numpy(v2).to(dev))
+    assert relmax(c2.cpu().numpy(), c2_ref) < RTOL
+    # host entry points: same kernels
+    rho_h, *sc = plan.rhoofr_lsd(d["c0"], d["f"], nsup)
+    assert np.array_equal(rho_h, rho.cpu().numpy()) and tuple(sc) == (ekin, rg, rr, cs, ca)
+    c2_h = 0.5 * d["c0"]
+    plan.vpsi_lsd(d["c0"], c2_h, d["f"], nsup, v2)
+    assert np.array_equal(c2_h, c2.cpu().numpy())
+    # raw partial channels of two groups + cpb_lsd_finish_dev == the single-group result
+    acc = torch.zeros_like(rho)
+    part = torch.empty_like(rho)
+    for g in range(2):
+        plan.rhoofr_lsd_dev(c0, d["f"], nsup, part, ngroups=2, my_group=g)
+        acc += part
+    rr2, cs2, ca2 = plan.lsd_finish_dev(acc)
+    assert np.abs(acc.cpu().numpy() - ref["rhoe"]).max() / scale < RTOL
+    assert abs(rr2 - ref["rsum_r"]) < ETOL and abs(cs2 - ref["csums"]) < ETOL and abs(ca2 - ref["csumsabs"]) < ETOL

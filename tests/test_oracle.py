@@ -162,3 +162,38 @@ def test_anisotropic_mesh():
     b = staged.rhoofr(g, c0, f, 1.0, 1.0)
     assert abs(a["rsum_r"] - a["rsum_g"]) < 1e-12
     assert np.abs(a["rhoe"] - b["rhoe"]).max() <= 1e-13 * np.abs(a["rhoe"]).max()
+
+
+def test_lsd_known_answers():
+    """LSD restatement (rhoofr_utils.mod.F90:375-385,543-559; vpsi_utils.mod.F90:450-482) pinned by
+    identities that follow from the reference formulas: the total density does not depend on the
+    spin labels; nsup = nstate / 0 put everything in one channel; csums is the alpha-beta charge;
+    each state's C2 is the non-LSD result with the potential of its own spin."""
+    geo = orc.make_geometry(16)
+    ns = 7
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    ref = orc.rhoofr(geo, c0, f, 1.0, 1.0)
+    occ = np.array([f[i] * orc.dotp(geo, c0[i], c0[i]) for i in range(ns)])
+    for nsup in (0, 3, 4, 7):
+        o = orc.rhoofr_lsd(geo, c0, f, 1.0, 1.0, nsup)
+        assert np.abs(o["rhoe"][0] - ref["rhoe"]).max() < 1e-13 * np.abs(ref["rhoe"]).max()
+        assert abs(o["rsum_r"] - ref["rsum_r"]) < 1e-12 and o["ekin"] == ref["ekin"]
+        assert abs(o["csums"] - (occ[:nsup].sum() - occ[nsup:].sum())) < 1e-11
+        assert o["csumsabs"] >= abs(o["csums"]) - 1e-12 and (o["rhoe"][1] >= 0).all()
+        if nsup == ns:
+            assert not o["rhoe"][1].any()
+    v2 = np.stack([v, 0.5 * v[::-1]])
+    a = orc.vpsi(geo, c0, np.zeros_like(c0), f, v2[0], 1.0)
+    b = orc.vpsi(geo, c0, np.zeros_like(c0), f, v2[1], 1.0)
+    for nsup in (0, 3, 4, 7):
+        o = orc.vpsi_lsd(geo, c0, np.zeros_like(c0), f, v2, 1.0, nsup)
+        exp = np.where((np.arange(ns) < nsup)[:, None], a, b)
+        assert np.abs(o - exp).max() < 1e-13 * np.abs(exp).max()
+    # groups: partial channels add up, finish after the sum (cp_grp_redist before :543)
+    acc = np.zeros((2, geo.nnr1))
+    for g in range(3):
+        acc += orc.rhoofr_lsd(geo, c0, f, 1.0, 1.0, 3, group=g, ngroups=3)["rhoe"]
+    full = orc.rhoofr_lsd(geo, c0, f, 1.0, 1.0, 3)
+    rr, cs, ca = orc.lsd_finish(geo, acc, 1.0)
+    assert np.abs(acc - full["rhoe"]).max() < 1e-13 * np.abs(full["rhoe"]).max()
+    assert abs(cs - full["csums"]) < 1e-12 and abs(ca - full["csumsabs"]) < 1e-12

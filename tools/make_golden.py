@@ -26,6 +26,12 @@ CASES = [
     ("n16_s7_grp1of3", (16, 16, 16), 7, "mixed", 1.0, 1.0, (1, 3)),
 ]
 
+LSD_CASES = [
+    # name, mesh, nstate, nsup, omega, tpiba2
+    ("n16_s7_nsup3", (16, 16, 16), 7, 3, 1.3, 0.9),
+    ("n20_s6_nsup4", (20, 20, 20), 6, 4, 1.0, 1.0),
+]
+
 
 def main():
     out = os.path.join(ROOT, "tests", "golden")
@@ -41,6 +47,20 @@ def main():
                             group=grp, ngroups=ngrp, rhoe=rho["rhoe"], ekin=rho["ekin"],
                             rsum_g=rho["rsum_g"], rsum_r=rho["rsum_r"], c2_in=c2_in, c2_out=c2)
         print(name, "ngw", geo.ngw, "nnr1", geo.nnr1)
+    # LSD (cntl%tlsd) fixtures live in tests/golden/lsd/
+    os.makedirs(os.path.join(out, "lsd"), exist_ok=True)
+    for name, nr, ns, nsup, omega, tpiba2 in LSD_CASES:
+        geo = orc.make_geometry(nr)
+        c0, f, v = orc.synthetic_inputs(geo, ns, seed=777 + ns + nr[0], f_pattern="mixed")
+        v2 = np.stack([v, 0.5 * v[::-1]])
+        rho = orc.rhoofr_lsd(geo, c0, f, omega, tpiba2, nsup)
+        c2_in = 0.25 * c0[::-1].copy()
+        c2 = orc.vpsi_lsd(geo, c0, c2_in, f, v2, tpiba2, nsup)
+        np.savez_compressed(os.path.join(out, "lsd", name + ".npz"), nr=np.array(nr), inyh=geo.inyh, hg=geo.hg,
+                            c0=c0, f=f, vpot=v2, omega=omega, tpiba2=tpiba2, nsup=nsup, rhoe=rho["rhoe"],
+                            ekin=rho["ekin"], rsum_g=rho["rsum_g"], rsum_r=rho["rsum_r"], csums=rho["csums"],
+                            csumsabs=rho["csumsabs"], c2_in=c2_in, c2_out=c2)
+        print("lsd/" + name, "ngw", geo.ngw)
 
 
 if __name__ == "__main__":
