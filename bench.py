@@ -262,6 +262,18 @@ def run_ours(args, rank, world, local):
     clocks = sampler.stop() if sampler else None
     value = 3.0 * nstate / (ms_step * 1e-3)
 
+    # ---- the same step with the device-side REAL SPACE WFN KEEP (CPB_PSI_KEEP / CPB_PSI_REUSE): vpsi
+    # starts from the y-pass output rhoofr left in HBM, i.e. nstate of the 3*nstate band-FFTs are not
+    # recomputed.  Reported separately as ms per CP step; `value` above never uses it.
+    def step_device_keep():
+        plan.rhoofr_dev(c0, f_block, rho, stream=stream, flags=lib.CPB_PSI_KEEP)
+        if world > 1:
+            cdist.cp_grp_redist(rho)
+            cdist.bcast_potential(v, src=0)
+        plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_PSI_REUSE)
+
+    ms_step_keep = timed(step_device_keep, max(1, min(args.steps, 3)), 1)
+
     # ---- per-kernel durations for the roofline: a separate pass with the kernels serialised on one
     # stream (cpb_plan_set_streams(1)) and every launch bracketed by CUDA events on that stream
     prof_steps = max(1, min(args.steps, 2))
@@ -342,6 +354,10 @@ def run_ours(args, rank, world, local):
                           "h2d_bytes_per_step": int(h2d - blk_bytes), "d2h_bytes_per_step": int(d2h),
                           "api": "as e2e, but cpb_vpsi(CPB_VPSI_OVERWRITE): the MD call site zeroes c2 first "
                                  "(forces_driver.mod.F90:175,224)"},
+        "psi_keep": {"ms_per_step": ms_step_keep,
+                     "note": "device-resident step with CPB_PSI_KEEP/CPB_PSI_REUSE (the analogue of CPMD's REAL SPACE WFN "
+                             "KEEP, rhoofr_utils.mod.F90:350-363): vpsi reuses rhoofr's y-pass output, "
+                             f"{cnt * 56.03e6 / 2 / 1e9 if n == 192 else 0:.1f} GB cache per rank; not used by `value`"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,

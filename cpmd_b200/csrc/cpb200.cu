@@ -98,7 +98,15 @@ struct cpb_plan {
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
-  double prologue_pairs = 0.5;  // block prologue cost in pair-times (pairs_per_group model)
+  // CPB_PSI_KEEP / CPB_PSI_REUSE: y-pass output of every pair of the last rhoofr call
+  cplx* T2keep = nullptr;
+  size_t t2keep_pairs = 0;   // capacity
+  size_t t2_pair = 0;        // elements of T2 per pair (all x tiles)
+  bool psi_valid = false;
+  int psi_npairs = 0;
+  const void* psi_key_ptr = nullptr;
+  long psi_key[5] = {0, 0, 0, 0, 0};  // ld, nstate, ngroups, my_group, nsup
+  double prologue_pairs = 0.25;  // block prologue cost in pair-times (pairs_per_group model)
   int x_sub = 16;         // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
@@ -188,6 +196,7 @@ void free_plan(cpb_plan* p) {
     rt::event_destroy(w.ev_rho);
   }
   rt::event_destroy(p->ev_fork);
+  rt::dfree(p->T2keep);
   rt::dfree(p->d_st1);
   rt::dfree(p->d_st2);
   rt::dfree(p->d_ca);
@@ -430,6 +439,40 @@ void join_streams(cpb_plan* p, cudaStream_t st, int nbatches) {
 // `pr`: the call's pair descriptors, already uploaded (upload_pairs) - the host-pointer entry points
 // do that BEFORE they enqueue their bulk H2D copies, because the copy engine serves all streams in
 // FIFO order and the first kernel would otherwise wait behind the whole upload.
+// ---- CPB_PSI_KEEP / CPB_PSI_REUSE -------------------------------------------------------------
+bool psi_key_match(const cpb_plan* p, const void* c0, long ld, int nstate, int ngroups, int my_group, int nsup,
+                   int npairs) {
+  return p->psi_valid && p->psi_key_ptr == c0 && p->psi_key[0] == ld && p->psi_key[1] == nstate &&
+         p->psi_key[2] == ngroups && p->psi_key[3] == my_group && p->psi_key[4] == nsup && p->psi_npairs == npairs;
+}
+void psi_key_set(cpb_plan* p, const void* c0, long ld, int nstate, int ngroups, int my_group, int nsup, int npairs) {
+  p->psi_key_ptr = c0;
+  p->psi_key[0] = ld;
+  p->psi_key[1] = nstate;
+  p->psi_key[2] = ngroups;
+  p->psi_key[3] = my_group;
+  p->psi_key[4] = nsup;
+  p->psi_npairs = npairs;
+  p->psi_valid = true;
+}
+// room for the y-pass output of `npairs` pairs; false (and no cache) if the device has no room
+bool psi_reserve(cpb_plan* p, int npairs) {
+  p->psi_valid = false;
+  if (p->chunk_xt != p->nxt) return false;  // the cache holds whole pairs
+  if ((size_t)npairs <= p->t2keep_pairs) return true;
+  rt::dfree(p->T2keep);
+  p->T2keep = nullptr;
+  p->t2keep_pairs = 0;
+  try {
+    p->T2keep = (cplx*)rt::dmalloc((size_t)npairs * p->t2_pair * sizeof(cplx));
+  } catch (const Error&) {
+    rt::check_last_clear();
+    return false;
+  }
+  p->t2keep_pairs = (size_t)npairs;
+  return true;
+}
+
 // batches never straddle the channel boundary: [0, n0) work on channel 0, [n0, np) on channel 1
 struct BatchSpan {
   int off, n, chan;
@@ -442,8 +485,9 @@ std::vector<BatchSpan> make_batches(const cpb_plan* p, int np, int n0) {
 }
 
 // rho0 / rho1: the density arrays of channel 0 / 1 (no LSD: n0 == np, rho1 unused)
+// keep: if non-null, pair i's y-pass output goes to keep + i * t2_pair and stays there (CPB_PSI_KEEP)
 void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, int n0, double* rho0, double* rho1,
-                cudaStream_t st, BatchHooks* hooks) {
+                cplx* keep, cudaStream_t st, BatchHooks* hooks) {
   const std::vector<BatchSpan> batches = make_batches(p, np, n0);
   const int nbatches = (int)batches.size();
   fork_streams(p, st, nbatches);
@@ -456,10 +500,11 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
     run_x_inv(p, w, c0, ldc, prb, nb);
     for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
       const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
-      { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
+      cplx* T2 = keep ? keep + (size_t)off * p->t2_pair : w.T2;
+      { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
       // rho is read-modify-written batch after batch: keep the order of the single-stream run
       if (b > 0 && p->nws > 1) rt::stream_wait(w.s, p->ws[(b - 1) % p->nws].ev_rho);
-      { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, w.T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
+      { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
       rt::event_record(w.ev_rho, w.s);
     }
     if (hooks) hooks->after_batch(b, off, nb, w.s);
@@ -469,8 +514,10 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
 }
 
 // v0 / v1: the potentials of channel 0 / 1 (no LSD: n0 == np, v1 unused)
+// reuse: if non-null, pair i starts from the kept y-pass output reuse + i * t2_pair (CPB_PSI_REUSE):
+// no gather, no x and y inverse passes; the z pass consumes the cache in place
 void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, int n0, const double* v0,
-              const double* v1, bool accumulate, cudaStream_t st, BatchHooks* hooks) {
+              const double* v1, bool accumulate, cplx* reuse, cudaStream_t st, BatchHooks* hooks) {
   const std::vector<BatchSpan> batches = make_batches(p, np, n0);
   const int nbatches = (int)batches.size();
   fork_streams(p, st, nbatches);
@@ -480,13 +527,14 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr
     cpb_plan::WorkSpace& w = p->ws[b % p->nws];
     if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
-    run_x_inv(p, w, c0, ldc, prb, nb);
+    if (!reuse) run_x_inv(p, w, c0, ldc, prb, nb);
     for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
       const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
       const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm);
-      { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
-      { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, w.T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
-      { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, w.T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      cplx* T2 = reuse ? reuse + (size_t)off * p->t2_pair : w.T2;
+      if (!reuse) { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
+      { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
     }
     run_x_fwd(p, w, c0, c2, ldc, prb, nb, accumulate);
     if (hooks) hooks->after_batch(b, off, nb, w.s);
@@ -533,13 +581,15 @@ void vpsi_coefs(const std::vector<PairHost>& pairs, const double* f, bool tksham
   }
 }
 
-void rho_coefs(cpb_plan* p, const std::vector<PairHost>& all, const double* f, std::vector<PairHost>& pairs,
-               std::vector<double>& ca, std::vector<double>& cb) {
+// keep_all: transform the unoccupied pairs too (they add nothing to rho, but CPB_PSI_KEEP wants the
+// y-pass output of every pair, like rsactive forces tfcal, rhoofr_utils.mod.F90:312)
+void rho_coefs(cpb_plan* p, const std::vector<PairHost>& all, const double* f, bool keep_all,
+               std::vector<PairHost>& pairs, std::vector<double>& ca, std::vector<double>& cb) {
   // rhoofr_utils.mod.F90:312-316 (skip a pair only if both occupations vanish), :369-374
   for (const PairHost& q : all) {
     const double f1 = f[q.s1];
     const double f2 = q.s2 >= 0 ? f[q.s2] : 0.0;
-    if (f1 == 0.0 && f2 == 0.0) continue;
+    if (f1 == 0.0 && f2 == 0.0 && !keep_all) continue;
     pairs.push_back(q);
     ca.push_back(f1 / p->omega);
     cb.push_back(f2 / p->omega);
@@ -793,6 +843,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     if (const char* e = std::getenv("CPB_PROLOGUE")) p->prologue_pairs = std::max(0.0, std::atof(e));
     p->x_sub = std::min(p->x_sub, p->max_batch);
     p->g_pair = (size_t)nxb * nrp;
+    p->t2_pair = (size_t)p->nxt * n2 * nzb * Bx;
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
@@ -949,12 +1000,16 @@ static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nsta
     std::vector<double> ca, cb;
     const bool lsd = nsup >= 0;
     const size_t nnr1 = p->nnr1();
-    rho_coefs(p, block_pairs(nstate, my_group, ngroups, nsup), f, pairs, ca, cb);
+    const std::vector<PairHost> all = block_pairs(nstate, my_group, ngroups, nsup);
+    const bool keep = (flags & CPB_PSI_KEEP) && psi_reserve(p, (int)all.size());
+    if (!keep) p->psi_valid = false;
+    rho_coefs(p, all, f, keep, pairs, ca, cb);
     ensure_red(p, kRedPerState * nblk + 3 * kSumBlocks);
     rt::dzero(rhoe_dev, (lsd ? 2 : 1) * nnr1 * sizeof(double), st);  // rhoofr_utils.mod.F90:198
     launch_kin(p, c0, ld_c0, first, nblk, st);                        // :178
     run_rhoofr(p, c0, ld_c0, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), count_chan0(pairs), rhoe_dev,
-               rhoe_dev + nnr1, st, nullptr);
+               rhoe_dev + nnr1, keep ? p->T2keep : nullptr, st, nullptr);
+    if (keep) psi_key_set(p, c0_dev, ld_c0, nstate, ngroups, my_group, nsup, (int)pairs.size());
     double* d_sums = p->d_red + kRedPerState * nblk;
     if (lsd) launch_lsd_sums(p, rhoe_dev, rhoe_dev + nnr1, nnr1, d_sums, ngroups == 1, st);  // :543-559
     else launch_sum(p, rhoe_dev, nnr1, d_sums, st);                                            // :607-619
@@ -1019,9 +1074,12 @@ static int vpsi_dev_impl(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld,
     std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups, nsup);
     std::vector<double> fi, fip1;
     vpsi_coefs(pairs, f, (flags & CPB_VPSI_TKSHAM) != 0, fi, fip1);
+    const bool reuse = (flags & CPB_PSI_REUSE) &&
+                       psi_key_match(p, c0_dev, ld, nstate, ngroups, my_group, nsup, (int)pairs.size());
+    p->psi_valid = false;  // the z pass consumes the cache in place
     run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, fip1, st), (int)pairs.size(),
              count_chan0(pairs), vpot_dev, vpot_dev + p->nnr1(),
-             !(flags & CPB_VPSI_OVERWRITE), st, nullptr);
+             !(flags & CPB_VPSI_OVERWRITE), reuse ? p->T2keep : nullptr, st, nullptr);
     rt::sync(st);
     resolve_spans(p);
     return CPB_OK;

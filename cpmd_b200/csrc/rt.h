@@ -37,6 +37,7 @@ inline void d2d(void* dst, const void* src, size_t n, cudaStream_t) { std::memcp
 inline void dzero(void* d, size_t n, cudaStream_t) { std::memset(d, 0, n); }
 inline void sync(cudaStream_t) {}
 inline void check_last(const char*) {}
+inline void check_last_clear() {}
 inline cudaStream_t stream_create() { return nullptr; }
 inline void stream_destroy(cudaStream_t) {}
 typedef void* event_t;
@@ -95,6 +96,7 @@ inline void d2d(void* dst, const void* src, size_t n, cudaStream_t s) {
 inline void dzero(void* d, size_t n, cudaStream_t s) { ck(cudaMemsetAsync(d, 0, n, s), "cudaMemsetAsync"); }
 inline void sync(cudaStream_t s) { ck(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 inline void check_last(const char* what) { ck(cudaGetLastError(), what); }
+inline void check_last_clear() { (void)cudaGetLastError(); }
 inline cudaStream_t stream_create() {
   cudaStream_t s;
   ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");

@@ -24,6 +24,8 @@ CPB_VPSI_TKSHAM = 2
 CPB_RHO_CHECK_CHARGE = 1
 CPB_C0_KEEP = 0x10
 CPB_C0_REUSE = 0x20
+CPB_PSI_KEEP = 0x40
+CPB_PSI_REUSE = 0x80
 
 
 class PlanInfo(C.Structure):

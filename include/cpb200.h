@@ -65,6 +65,15 @@ typedef enum {
 /* host-pointer entry points only: device-side cache of the group's c0 block */
 #define CPB_C0_KEEP 0x10u  /* after this call the uploaded block stays valid on the device */
 #define CPB_C0_REUSE 0x20u /* skip the upload if (c0 pointer, ld, nstate, group) match the kept block */
+/* all entry points: device-side counterpart of CPMD's REAL SPACE WFN KEEP (rsactive: rhoofr stores
+ * the real-space wavefunctions in rswf, rhoofr_utils.mod.F90:350-363, so that later FFTs of the same
+ * orbitals can be skipped).  cpb_rhoofr* with CPB_PSI_KEEP leaves the y-pass output of every pair of
+ * the block (16*n1*n2*zband bytes per pair, half the size of psi(r)) in HBM; the next cpb_vpsi* call
+ * with CPB_PSI_REUSE and the same (c0 pointer, ld, nstate, group, nsup) starts from it - no gather, no
+ * x and y inverse passes - and consumes it.  The caller vouches that c0 did not change in between
+ * (MD step: forces_driver.mod.F90:165 -> :224).  Silently ignored when the device has no room. */
+#define CPB_PSI_KEEP 0x40u
+#define CPB_PSI_REUSE 0x80u
 
 typedef struct {
   int nr[3];          /* mesh */

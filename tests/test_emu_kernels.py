@@ -269,3 +269,41 @@ def test_lsd_groups_and_context(emu_cdll):
     assert relmax(c2b, c2_full) < RTOL
     with pytest.raises(CpbError):
         p.rhoofr_lsd(d["c0"], d["f"], ns + 1)
+
+
+def test_psi_keep_reuse(emu_cdll):
+    """CPB_PSI_KEEP / CPB_PSI_REUSE (device-side REAL SPACE WFN KEEP): vpsi starts from the y-pass
+    output rhoofr left behind; same kernels on the same data, so the result is bit-identical."""
+    d = synthetic.make_inputs(20, 7, f_pattern="mixed")          # has unoccupied states
+    p = _plan(d, emu_cdll, max_batch=2)
+    rho0, *s0 = p.rhoofr(d["c0"], d["f"])
+    a = 0.5 * d["c0"]
+    p.vpsi(d["c0"], a, d["f"], d["vpot"])
+    rho1, *s1 = p.rhoofr(d["c0"], d["f"], flags=lib.CPB_C0_KEEP | lib.CPB_PSI_KEEP)
+    assert np.array_equal(rho0, rho1) and s0 == s1
+    b = 0.5 * d["c0"]
+    n0 = p.launch_count
+    p.vpsi(d["c0"], b, d["f"], d["vpot"], flags=lib.CPB_C0_REUSE | lib.CPB_PSI_REUSE)
+    reuse_launches = p.launch_count - n0
+    assert np.array_equal(a, b)
+    # the cache is consumed: a second REUSE call runs the full pipeline, same answer
+    c = 0.5 * d["c0"]
+    n0 = p.launch_count
+    p.vpsi(d["c0"], c, d["f"], d["vpot"], flags=lib.CPB_C0_REUSE | lib.CPB_PSI_REUSE)
+    assert np.array_equal(a, c) and p.launch_count - n0 > reuse_launches
+    # a different array never hits the cache
+    p.rhoofr(d["c0"], d["f"], flags=lib.CPB_C0_KEEP | lib.CPB_PSI_KEEP)
+    other = d["c0"] * (1.0 + 0.5j)
+    e = np.zeros_like(other)
+    p.vpsi(other, e, d["f"], d["vpot"], flags=lib.CPB_C0_REUSE | lib.CPB_PSI_REUSE)
+    geo = orc.make_geometry(20)
+    assert relmax(e, orc.vpsi(geo, other, np.zeros_like(other), d["f"], d["vpot"], 1.0)) < RTOL
+    # LSD and groups go through the same cache
+    v2 = np.stack([d["vpot"], 0.5 * d["vpot"]])
+    ref = np.zeros_like(d["c0"])
+    got = np.zeros_like(d["c0"])
+    for g in range(2):
+        p.vpsi_lsd(d["c0"], ref, d["f"], 3, v2, ngroups=2, my_group=g)
+        p.rhoofr_lsd(d["c0"], d["f"], 3, ngroups=2, my_group=g, flags=lib.CPB_C0_KEEP | lib.CPB_PSI_KEEP)
+        p.vpsi_lsd(d["c0"], got, d["f"], 3, v2, ngroups=2, my_group=g, flags=lib.CPB_C0_REUSE | lib.CPB_PSI_REUSE)
+    assert np.array_equal(ref, got)

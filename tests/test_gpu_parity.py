@@ -240,3 +240,25 @@ def test_lsd_device_and_host(dev, n, nstate, nsup, mb):
     rr2, cs2, ca2 = plan.lsd_finish_dev(acc)
     assert np.abs(acc.cpu().numpy() - ref["rhoe"]).max() / scale < RTOL
     assert abs(rr2 - ref["rsum_r"]) < ETOL and abs(cs2 - ref["csums"]) < ETOL and abs(ca2 - ref["csumsabs"]) < ETOL
+
+
+def test_psi_keep_reuse_device(dev):
+    """CPB_PSI_KEEP / CPB_PSI_REUSE on the device entry points: bit-identical, fewer launches."""
+    n, ns = 64, 12
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    v = torch.from_numpy(d["vpot"]).to(dev)
+    rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    rho_k = torch.empty_like(rho)
+    s0 = plan.rhoofr_dev(c0, d["f"], rho)
+    a = 0.5 * c0
+    n0 = plan.launch_count
+    plan.vpsi_dev(c0, a, d["f"], v)
+    full = plan.launch_count - n0
+    s1 = plan.rhoofr_dev(c0, d["f"], rho_k, flags=lib.CPB_PSI_KEEP)
+    assert torch.equal(rho, rho_k) and s0 == s1
+    b = 0.5 * c0
+    n0 = plan.launch_count
+    plan.vpsi_dev(c0, b, d["f"], v, flags=lib.CPB_PSI_REUSE)
+    assert torch.equal(a, b) and plan.launch_count - n0 < full
