@@ -271,6 +271,65 @@ class Plan:
         self._check(rc)
         return c2
 
+    # -- dense transforms on the density cutoff + local part of vofrho (plan built from nhg) --------
+    # Arrays follow the package convention: Fortran (ld, nfields) = C-order (nfields, ld).
+    def _dense_shapes(self, f, g):
+        nf = 1 if g.ndim == 1 else int(g.shape[0])
+        ld = int(g.shape[-1])
+        n_f = f.numel() if _is_torch(f) else f.size
+        if ld < self.ngw or n_f < nf * self.nnr1:
+            raise ValueError("array shapes inconsistent with the plan (ngw, nnr1)")
+        return nf, ld
+
+    def dense_fwfft_dev(self, f, g, stream=None):
+        """``cpb_dense_fwfft_dev``: f float64 CUDA (nfields, nnr1) -> g complex128 CUDA (nfields, ld):
+        fwfftn(v,.FALSE.) + gather through nzh (vofrhoa_utils.mod.F90:88-95)."""
+        nf, ld = self._dense_shapes(f, g)
+        self._check(self._L.cpb_dense_fwfft_dev(self._h, _ptr(f), nf, _ptr(g), ld, _stream_ptr(stream)))
+        return g
+
+    def dense_invfft_dev(self, g, f, accumulate=False, stream=None):
+        """``cpb_dense_invfft_dev``: g (nfields, ld) -> f (nfields, nnr1) = REAL/AIMAG of
+        invfftn(v,.FALSE.) of the scattered coefficients (vofrhob_utils.mod.F90:155-173)."""
+        nf, ld = self._dense_shapes(f, g)
+        flags = _lib.CPB_DENSE_ACCUMULATE if accumulate else 0
+        self._check(self._L.cpb_dense_invfft_dev(self._h, _ptr(g), ld, nf, _ptr(f), flags, _stream_ptr(stream)))
+        return f
+
+    @staticmethod
+    def _ener_dict(e):
+        return dict(eh=complex(e[0], e[1]), ei=complex(e[2], e[3]), ee=complex(e[4], e[5]),
+                    eps=complex(e[6], e[7]), vploc=e[8])
+
+    def vofrho_local_dev(self, rhoe, scg, eivps, eirop, v, rhog=None, vtemp=None, stream=None):
+        """``cpb_vofrho_local_dev`` (CUDA tensors): rhoe -> rhog -> ppener -> v(r); v may be rhoe.
+        Returns dict(eh, ei, ee, eps (complex), vploc) (ppener_utils.mod.F90:23-108)."""
+        for a in (scg, eivps, eirop):
+            if a.numel() < self.ngw:
+                raise ValueError("scg / eivps / eirop need nhg entries")
+        if rhoe.numel() < self.nnr1 or v.numel() < self.nnr1:
+            raise ValueError("rhoe / v too small")
+        e = (C.c_double * 9)()
+        self._check(self._L.cpb_vofrho_local_dev(self._h, _ptr(rhoe), _ptr(scg), _ptr(eivps), _ptr(eirop),
+                                                 _ptr(rhog), _ptr(vtemp), _ptr(v), e, _stream_ptr(stream)))
+        return self._ener_dict(e)
+
+    def vofrho_local(self, rhoe, scg, eivps, eirop, v=None, rhog=None, vtemp=None):
+        """``cpb_vofrho_local`` (host arrays).  Returns (v, energies dict)."""
+        rh = _as_host(rhoe, np.float64)
+        scg = np.ascontiguousarray(scg, dtype=np.float64)
+        eivps = np.ascontiguousarray(eivps, dtype=np.complex128)
+        eirop = np.ascontiguousarray(eirop, dtype=np.complex128)
+        if min(scg.size, eivps.size, eirop.size) < self.ngw or rh.size < self.nnr1:
+            raise ValueError("array shapes inconsistent with the plan (ngw, nnr1)")
+        if v is None:
+            v = np.empty(self.nnr1, dtype=np.float64)
+        vh = _as_host(v, np.float64)
+        e = (C.c_double * 9)()
+        self._check(self._L.cpb_vofrho_local(self._h, rh.ctypes.data, scg.ctypes.data, eivps.ctypes.data,
+                                             eirop.ctypes.data, _ptr(rhog), _ptr(vtemp), vh.ctypes.data, e))
+        return v, self._ener_dict(e)
+
 
 def _as_host(a, dtype):
     """numpy view of a host array (numpy, or a CPU/pinned torch tensor) without copying."""

@@ -32,6 +32,11 @@ struct AxisKernels {
                 int xt0, int nxc, bool half);
   void (*z_vpsi)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
                  int ppg, bool half);
+  // dense transforms (real fields on the density-cutoff sphere): z passes with phasen
+  void (*z_fwd_real)(cudaStream_t, const double* fre, const double* fim, cplx* T2, const PlanDev&, int xt0, int nxc,
+                     bool half);
+  void (*z_inv_real)(cudaStream_t, const cplx* T2, double* ore, double* oim, const PlanDev&, int xt0, int nxc,
+                     bool acc, bool half);
   int yz_blocks_per_sm;  // occupancy the y/z kernels are compiled for
   int x_inv_blocks, x_fwd_blocks;  // same for the x kernels
 };

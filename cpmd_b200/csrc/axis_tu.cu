@@ -124,8 +124,34 @@ void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, in
   else z_vpsi_t<false>(st, T2, vpot, pd, npair, xt0, nxc, ppg);
 }
 
+template <bool HALF>
+void z_fwd_real_t(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0,
+                  int nxc) {
+  auto k = k_z_fwd_real<R1, R2, B, HALF>;
+  allow_smem(k, kSmemYZ);
+  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, fre, fim, T2, pd, xt0);
+}
+void z_fwd_real(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0, int nxc,
+                bool half) {
+  if (half) z_fwd_real_t<true>(st, fre, fim, T2, pd, xt0, nxc);
+  else z_fwd_real_t<false>(st, fre, fim, T2, pd, xt0, nxc);
+}
+
+template <bool HALF>
+void z_inv_real_t(cudaStream_t st, const cplx* T2, double* ore, double* oim, const PlanDev& pd, int xt0, int nxc,
+                  bool acc) {
+  auto k = k_z_inv_real<R1, R2, B, HALF>;
+  allow_smem(k, kSmemYZ);
+  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, T2, ore, oim, pd, xt0, acc ? 1 : 0);
+}
+void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const PlanDev& pd, int xt0, int nxc,
+                bool acc, bool half) {
+  if (half) z_inv_real_t<true>(st, T2, ore, oim, pd, xt0, nxc, acc);
+  else z_inv_real_t<false>(st, T2, ore, oim, pd, xt0, nxc, acc);
+}
+
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
-                            x_inv, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, YZBlocks<R1, R2>::v,
+                            x_inv, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real, YZBlocks<R1, R2>::v,
                             XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD};
 
 }  // namespace

@@ -153,6 +153,10 @@ struct cpb_plan {
   int d_real_cols = 0;
   cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
   std::vector<rt::event_t> ev_in, ev_done;
+  // dense-transform staging (cpb_vofrho_local, host-pointer dense entry points)
+  cplx* d_gbuf = nullptr;  // G-space scratch, d_gbuf_cap elements
+  size_t d_gbuf_cap = 0;
+  double* d_scg = nullptr;  // [ngw]
   // c0 cache key
   const void* c0_key_ptr = nullptr;
   long c0_key_ld = 0;
@@ -207,6 +211,8 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_c0);
   rt::dfree(p->d_c2);
   rt::dfree(p->d_real);
+  rt::dfree(p->d_gbuf);
+  rt::dfree(p->d_scg);
   for (auto& sp : p->spans) {
     rt::event_destroy(sp.a);
     rt::event_destroy(sp.b);
@@ -1099,6 +1105,185 @@ int cpb_vpsi_lsd_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int
                      const double* vpot_dev, int ngroups, int my_group, unsigned flags, void* stream) {
   if (nsup < 0) return fail(CPB_ERR_INVALID, "negative nsup");
   return vpsi_dev_impl(p, c0_dev, c2_dev, ld, nstate, f, nsup, vpot_dev, ngroups, my_group, flags, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Dense transforms of real fields on the plan's G list (a plan created from the nhg vectors of
+// the density cutoff) and the local part of vofrho.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+void ensure_gbuf(cpb_plan* p, size_t elems) {
+  if (elems <= p->d_gbuf_cap) return;
+  rt::dfree(p->d_gbuf);
+  p->d_gbuf = nullptr;
+  p->d_gbuf_cap = 0;
+  p->d_gbuf = (cplx*)rt::dmalloc(elems * sizeof(cplx));
+  p->d_gbuf_cap = elems;
+}
+
+// fwfftn(v,.FALSE.) of nf real fields + zgthr through nzh: f (nnr1, nf) -> g (ld, nf)
+void run_dense_fw(cpb_plan* p, const double* f, int nf, cplx* g, long ld, cudaStream_t st) {
+  cpb_plan::WorkSpace& w = p->ws[0];
+  const double* fim = nf == 2 ? f + p->nnr1() : nullptr;
+  for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+    const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+    { Timed t(p, st, CPB_K_DENSE); p->kz->z_fwd_real(st, f, fim, w.T2, p->pd, xt0, nxc, p->half_z); }
+    { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, w.T2, w.T1, p->pd, 1, xt0, nxc, 1, p->half_y); }
+  }
+  { Timed t(p, st, CPB_K_X_FWD); p->kx->x_fwd(st, w.T1, w.G, p->pd, 1, 1, p->half_x); }
+  Timed t(p, st, CPB_K_DENSE);
+  auto k = k_gather_g;
+  CPB_LAUNCH(k, dim3((p->ngw + 255) / 256), dim3(256), 0, st, (const cplx*)w.G, p->pd, g, nf == 2 ? g + ld : nullptr);
+}
+
+// scatter through nzh / indz + invfftn(v,.FALSE.) + REAL(): g (ld, nf) -> f (nnr1, nf)
+void run_dense_inv(cpb_plan* p, const cplx* g, long ld, int nf, double* f, bool acc, cudaStream_t st) {
+  cpb_plan::WorkSpace& w = p->ws[0];
+  std::vector<PairHost> pairs(1);
+  pairs[0].s1 = 0;
+  pairs[0].s2 = nf == 2 ? 1 : -1;
+  const std::vector<double> zero(1, 0.0);
+  const PairDev pr = upload_pairs(p, pairs, zero, zero, st);
+  double* fim = nf == 2 ? f + p->nnr1() : nullptr;
+  if (!acc) rt::dzero(f, (size_t)nf * p->nnr1() * sizeof(double), st);  // pads
+  { Timed t(p, st, CPB_K_X_INV); p->kx->x_inv(st, g, ld, w.T1, p->pd, pr, 1, 1, p->half_x); }
+  for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+    const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+    { Timed t(p, st, CPB_K_Y_INV); p->ky->y_inv(st, w.T1, w.T2, p->pd, 1, xt0, nxc, 1, p->half_y); }
+    { Timed t(p, st, CPB_K_DENSE); p->kz->z_inv_real(st, w.T2, f, fim, p->pd, xt0, nxc, acc, p->half_z); }
+  }
+}
+
+int check_dense(cpb_plan* p, const void* a, const void* b, long ld, int nf) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  if (!a || !b) return fail(CPB_ERR_INVALID, "null array");
+  if (nf != 1 && nf != 2) return fail(CPB_ERR_INVALID, "nfields must be 1 or 2");
+  if (ld < p->ngw) return fail(CPB_ERR_INVALID, "leading dimension smaller than the plan's G count");
+  return 0;
+}
+
+// enqueue the local part of vofrho on `st`; the partial sums land in p->d_red[0 .. 8*kSumBlocks)
+void run_vofrho_local(cpb_plan* p, const double* rhoe, const double* scg, const cplx* eivps, const cplx* eirop,
+                      cplx* rhog, cplx* vtemp, double* v, cudaStream_t st) {
+  run_dense_fw(p, rhoe, 1, rhog, p->ngw, st);                      // vofrhoa_utils.mod.F90:88-95
+  {
+    Timed t(p, st, CPB_K_DENSE);
+    auto k = k_ppener;                                             // :102 -> ppener_utils.mod.F90:23-108
+    CPB_LAUNCH(k, dim3(kSumBlocks), dim3(256), 8 * 256 * sizeof(double), st, (const cplx*)rhog, scg, eivps, eirop,
+               vtemp, p->ngw, p->geq0, p->d_red);
+  }
+  run_dense_inv(p, vtemp, p->ngw, 1, v, false, st);                // vofrhob_utils.mod.F90:155-173
+}
+
+void finish_vofrho_scalars(cpb_plan* p, double eivps0_re, double* ener) {
+  if (!ener) return;
+  for (int j = 0; j < 8; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < kSumBlocks; ++i) s += p->h_red[(size_t)j * kSumBlocks + i];
+    ener[j] = s;
+  }
+  ener[8] = p->geq0 ? eivps0_re : 0.0;  // vploc (ppener_utils.mod.F90:59-60,73)
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb_dense_fwfft_dev(cpb_plan* p, const double* f_dev, int nfields, void* g_dev, long ld, void* stream) {
+  if (int e = check_dense(p, f_dev, g_dev, ld, nfields)) return e;
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    run_dense_fw(p, f_dev, nfields, (cplx*)g_dev, ld, st);
+    rt::check_last("dense forward kernels");
+    rt::sync(st);
+    resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
+}
+
+int cpb_dense_invfft_dev(cpb_plan* p, const void* g_dev, long ld, int nfields, double* f_dev, unsigned flags,
+                         void* stream) {
+  if (int e = check_dense(p, g_dev, f_dev, ld, nfields)) return e;
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    run_dense_inv(p, (const cplx*)g_dev, ld, nfields, f_dev, (flags & CPB_DENSE_ACCUMULATE) != 0, st);
+    rt::check_last("dense inverse kernels");
+    rt::sync(st);
+    resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
+}
+
+int cpb_vofrho_local_dev(cpb_plan* p, const double* rhoe_dev, const double* scg_dev, const void* eivps_dev,
+                         const void* eirop_dev, void* rhog_dev, void* vtemp_dev, double* v_dev, double* ener,
+                         void* stream) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  if (!rhoe_dev || !scg_dev || !eivps_dev || !eirop_dev || !v_dev) return fail(CPB_ERR_INVALID, "null array");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ensure_red(p, 8 * kSumBlocks + 2);
+    ensure_gbuf(p, 2 * (size_t)p->ngw);
+    cplx* rhog = rhog_dev ? (cplx*)rhog_dev : p->d_gbuf;
+    cplx* vtemp = vtemp_dev ? (cplx*)vtemp_dev : p->d_gbuf + p->ngw;
+    run_vofrho_local(p, rhoe_dev, scg_dev, (const cplx*)eivps_dev, (const cplx*)eirop_dev, rhog, vtemp, v_dev, st);
+    rt::check_last("vofrho kernels");
+    rt::d2h(p->h_red, p->d_red, (size_t)8 * kSumBlocks * sizeof(double), st);
+    rt::d2h(p->h_red + 8 * kSumBlocks, eivps_dev, sizeof(cplx), st);
+    rt::sync(st);
+    resolve_spans(p);
+    finish_vofrho_scalars(p, p->h_red[8 * kSumBlocks], ener);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
+}
+
+int cpb_vofrho_local(cpb_plan* p, const double* rhoe, const double* scg, const void* eivps, const void* eirop,
+                     void* rhog, void* vtemp, double* v, double* ener) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  if (!rhoe || !scg || !eivps || !eirop || !v) return fail(CPB_ERR_INVALID, "null array");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = p->s_main;
+    const size_t ng = (size_t)p->ngw, nnr1 = p->nnr1();
+    ensure_red(p, 8 * kSumBlocks + 2);
+    ensure_gbuf(p, 4 * ng);  // rhog, vtemp, eivps, eirop
+    if (!p->d_scg) p->d_scg = (double*)rt::dmalloc(ng * sizeof(double));
+    if (!p->d_real || p->d_real_cols < 1) {
+      rt::dfree(p->d_real);
+      p->d_real = nullptr;
+      p->d_real = (double*)rt::dmalloc(nnr1 * sizeof(double));
+      p->d_real_cols = 1;
+    }
+    cplx *d_rhog = p->d_gbuf, *d_vtemp = p->d_gbuf + ng, *d_vps = p->d_gbuf + 2 * ng, *d_rop = p->d_gbuf + 3 * ng;
+    rt::h2d(p->d_real, rhoe, nnr1 * sizeof(double), st);
+    rt::h2d(p->d_scg, scg, ng * sizeof(double), st);
+    rt::h2d(d_vps, eivps, ng * sizeof(cplx), st);
+    rt::h2d(d_rop, eirop, ng * sizeof(cplx), st);
+    // rho and V share the array, like the reference's rhoe (in: density, out: potential)
+    run_vofrho_local(p, p->d_real, p->d_scg, d_vps, d_rop, d_rhog, d_vtemp, p->d_real, st);
+    rt::check_last("vofrho kernels");
+    rt::d2h(p->h_red, p->d_red, (size_t)8 * kSumBlocks * sizeof(double), st);
+    rt::d2h(v, p->d_real, nnr1 * sizeof(double), st);
+    if (rhog) rt::d2h(rhog, d_rhog, ng * sizeof(cplx), st);
+    if (vtemp) rt::d2h(vtemp, d_vtemp, ng * sizeof(cplx), st);
+    rt::sync(st);
+    resolve_spans(p);
+    finish_vofrho_scalars(p, ((const double*)eivps)[0], ener);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
 }
 
 }  // extern "C"

@@ -756,4 +756,97 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// z passes of the DENSE transforms (fftnew with sparse = .FALSE., fftmain_utils.mod.F90:105-120,
+// 137-153), used for the density / potential on the density-cutoff sphere (vofrho's local part,
+// vofrhoa_utils.mod.F90:88-95, vofrhob_utils.mod.F90:155-173).  A plan built from the nhg list of
+// the density cutoff runs them with the same x/y kernels as the wavefunction path; what differs
+// is the real-space side: REAL fields (one, or two packed as Re / Im of one complex transform),
+// and phasen's factor (-1)^(x+y+z) (fftutil_utils.mod.F90:479-503), which moves G = 0 from the box
+// centre used by the index maps to the origin.  One transform per call: no pair loop, plain
+// global loads.  grid = (x tiles of the chunk, n2), block = B * max(R1,R2)
+// ---------------------------------------------------------------------------------------------
+// forward: f(r) -> phasen -> z FFT (e^{-i...}) -> band of T2
+template <int R1, int R2, int B, bool HALF>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
+    k_z_fwd_real(const double* CPB_RESTRICT fre, const double* CPB_RESTRICT fim, cplx* CPB_RESTRICT T2, PlanDev pd,
+                 int xt0) {
+  using KR = KRange<R1, HALF>;
+  CPB_DYN_SMEM(cplx, S);
+  const int tid = threadIdx.x;
+  const int b = tid % B, r = tid / B;
+  const int xtc = blockIdx.x;
+  const int x = (xt0 + xtc) * B + b;
+  const int y = blockIdx.y;
+  const bool xok = x < pd.n1;
+  const int zlo = pd.zlo, nzb = pd.nzb;
+  cplx* Sf = S + b;
+  if (r < R1) {
+    cplx u[R2];
+    static_for<0, R2>([&](auto qq) {
+      constexpr int q = decltype(qq)::value;
+      const int z = r + R1 * q;
+      const size_t o = ((size_t)z * pd.kr2 + y) * pd.kr1 + x;
+      const double sg = ((x + y + z) & 1) ? -1.0 : 1.0;
+      u[q] = xok ? mk(sg * fre[o], fim ? sg * fim[o] : 0.0) : mk(0.0, 0.0);
+    });
+    pass_a<R2, R1, false>(u, r, pd.tw3, Sf, B);
+  }
+  __syncthreads();
+  if (r < R2) {
+    cplx w[R1];
+    pass_b<R2, R1, false>(w, r, Sf, B);
+    cplx* d = T2 + ((size_t)xtc * pd.n2 + y) * nzb * B + b;
+    static_for<KR::lo, KR::hi>([&](auto kk) {
+      constexpr int k = decltype(kk)::value;
+      const int zr = r + R2 * k - zlo;
+      if (zr >= 0 && zr < nzb) d[zr * B] = w[k];
+    });
+  }
+}
+
+// inverse: band of T2 -> z FFT (e^{+i...}) -> phasen -> Re to ore, Im to oim (if non-null);
+// acc != 0: added to the arrays instead of stored
+template <int R1, int R2, int B, bool HALF>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
+    k_z_inv_real(const cplx* CPB_RESTRICT T2, double* ore, double* oim, PlanDev pd, int xt0, int acc) {
+  using KR = KRange<R1, HALF>;
+  CPB_DYN_SMEM(cplx, S);
+  const int tid = threadIdx.x;
+  const int b = tid % B, r = tid / B;
+  const int xtc = blockIdx.x;
+  const int x = (xt0 + xtc) * B + b;
+  const int y = blockIdx.y;
+  const bool xok = x < pd.n1;
+  const int zlo = pd.zlo, nzb = pd.nzb;
+  cplx* Sb = S + b;
+  if (r < R2) {
+    const cplx* in = T2 + ((size_t)xtc * pd.n2 + y) * nzb * B + b;
+    cplx v[R1];
+    static_for<0, R1>([&](auto kk) {
+      constexpr int k = decltype(kk)::value;
+      if constexpr (k >= KR::lo && k < KR::hi) {
+        const int zr = r + R2 * k - zlo;
+        v[k] = (zr >= 0 && zr < nzb) ? in[zr * B] : mk(0.0, 0.0);
+      } else {
+        v[k] = mk(0.0, 0.0);
+      }
+    });
+    pass_a_in<R1, R2, true, KR::lo, KR::hi>(v, r, pd.tw3, Sb, B);
+  }
+  __syncthreads();
+  if (r < R1 && xok) {
+    cplx u[R2];
+    pass_b<R1, R2, true>(u, r, Sb, B);
+    static_for<0, R2>([&](auto qq) {
+      constexpr int q = decltype(qq)::value;
+      const int z = r + R1 * q;
+      const size_t o = ((size_t)z * pd.kr2 + y) * pd.kr1 + x;
+      const double sg = ((x + y + z) & 1) ? -1.0 : 1.0;
+      ore[o] = (acc ? ore[o] : 0.0) + sg * u[q].x;
+      if (oim) oim[o] = (acc ? oim[o] : 0.0) + sg * u[q].y;
+    });
+  }
+}
+
 }  // namespace cpb

@@ -142,4 +142,81 @@ CPB_GLOBAL k_unpack(const cplx* CPB_RESTRICT G, const cplx* CPB_RESTRICT c0, cpl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense transforms, G side.  k_gather_g: the counterpart of zgthr(nhg, v, vtemp, nzh)
+// (vofrhob_utils.mod.F90:240,245; rhog(ig) = v(nzh(ig)) in ppener_utils.mod.F90:91) on the band-ray
+// storage written by k_x_fwd.  One real field: a(G) = P(+G), exactly what the reference reads.  Two
+// real fields packed as Re / Im of one transform (p = a + i b): a(G) = [P(G) + conj P(-G)] / 2,
+// b(G) = [P(G) - conj P(-G)] / (2i).   grid = ceil(ngw/256), block = 256
+// ---------------------------------------------------------------------------------------------
+CPB_GLOBAL k_gather_g(const cplx* CPB_RESTRICT G, PlanDev pd, cplx* CPB_RESTRICT ga, cplx* CPB_RESTRICT gb) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const cplx pp = G[pd.gpos[ig]];
+  if (!gb) {
+    ga[ig] = pp;
+    return;
+  }
+  const cplx pm = G[pd.gneg[ig]];
+  ga[ig] = mk(0.5 * (pp.x + pm.x), 0.5 * (pp.y - pm.y));
+  gb[ig] = mk(0.5 * (pp.y + pm.y), 0.5 * (pm.x - pp.x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_ppener: ppener (ppener_utils.mod.F90:23-108).  vtemp(ig) = scg(ig) * (rhog(ig) + eirop(ig)) +
+// eivps(ig) and the four complex sums eh, ei, ee, eps; the G = 0 entry (geq0, ig = 0) follows the
+// reference's special case (:58-70): half weights, vtemp(1) = scg(1) * rhog without the
+// pseudopotential term.  Per-block partials in a fixed order (bit-stable):
+// partial[(j*gridDim.x + block)] for j = 0..7 = Re eh, Im eh, Re ei, Im ei, Re ee, Im ee, Re eps,
+// Im eps.  block = 256
+// ---------------------------------------------------------------------------------------------
+CPB_GLOBAL k_ppener(const cplx* CPB_RESTRICT rhog, const double* CPB_RESTRICT scg, const cplx* CPB_RESTRICT eivps,
+                    const cplx* CPB_RESTRICT eirop, cplx* CPB_RESTRICT vtemp, int nhg, int geq0,
+                    double* CPB_RESTRICT partial) {
+  CPB_DYN_SMEM(double, red);  // 8*256
+  const int tid = threadIdx.x;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int ig = blockIdx.x * 256 + tid; ig < nhg; ig += gridDim.x * 256) {
+    const cplx vp = eivps[ig], rp = eirop[ig], rhet = rhog[ig];
+    const cplx rg = cadd(rhet, rp);
+    const double sc = scg[ig];
+    if (ig == 0 && geq0) {
+      const cplx e = cscale(cmulc(vp, rhet), 0.5);  // 0.5 * vp * conj(rhet)
+      s[6] += e.x;
+      s[7] += e.y;
+      s[0] += 0.5 * sc * rg.x * rg.x;               // 0.5 * scg * Re(rhog)^2
+      const cplx i2 = cscale(cmul(rp, rp), 0.5 * sc);
+      s[2] += i2.x;
+      s[3] += i2.y;
+      const cplx e2 = cscale(cmul(rhet, rhet), 0.5 * sc);
+      s[4] += e2.x;
+      s[5] += e2.y;
+      vtemp[ig] = cscale(rg, sc);
+    } else {
+      const cplx vcg = cscale(rg, sc);
+      vtemp[ig] = cadd(vcg, vp);
+      const cplx h = cmulc(vcg, rg);  // vcg * conj(rhog)
+      s[0] += h.x;
+      s[1] += h.y;
+      const cplx i2 = cscale(cmulc(rp, rp), sc);
+      s[2] += i2.x;
+      s[3] += i2.y;
+      const cplx e2 = cscale(cmulc(rhet, rhet), sc);
+      s[4] += e2.x;
+      s[5] += e2.y;
+      const cplx e = cmulc(vp, rhet);  // conj(rhet) * vp
+      s[6] += e.x;
+      s[7] += e.y;
+    }
+  }
+  for (int j = 0; j < 8; ++j) red[j * 256 + tid] = s[j];
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (tid < k)
+      for (int j = 0; j < 8; ++j) red[j * 256 + tid] += red[j * 256 + tid + k];
+    __syncthreads();
+  }
+  if (tid < 8) partial[(size_t)tid * gridDim.x + blockIdx.x] = red[tid * 256];
+}
+
 }  // namespace cpb

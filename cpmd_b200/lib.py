@@ -26,6 +26,7 @@ CPB_C0_KEEP = 0x10
 CPB_C0_REUSE = 0x20
 CPB_PSI_KEEP = 0x40
 CPB_PSI_REUSE = 0x80
+CPB_DENSE_ACCUMULATE = 1
 
 
 class PlanInfo(C.Structure):
@@ -84,13 +85,20 @@ SYMBOLS = {
                                  C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
     "cpb_vpsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "cpb_dense_fwfft_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p]),
+    "cpb_dense_invfft_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
+    "cpb_vofrho_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "cpb_vofrho_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),
 }
 
-KERNEL_KINDS = ("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd", "kin_energy", "rho_sum", "unpack")
+KERNEL_KINDS = ("x_inv", "y_inv", "z_rho", "z_vpsi", "y_fwd", "x_fwd", "kin_energy", "rho_sum", "unpack",
+                "dense")
 
 
 def declare(cdll: C.CDLL) -> C.CDLL:

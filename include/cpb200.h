@@ -176,6 +176,42 @@ int cpb_vpsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int 
                  const double* f, const double* vpot_dev, int ngroups, int my_group,
                  unsigned flags, void* stream);
 
+/* ---- dense transforms on the density cutoff and the local part of vofrho -------------------
+ * (the step between rhoofr and vpsi.)  These run on a plan created by cpb_plan_create
+ * from the nhg vectors of the DENSITY cutoff: ngw := ncpw%nhg, inyh(3,nhg), hg(nhg) - the same
+ * cppt arrays, whose first ngw entries are the wavefunction sphere - so that the plan's maps are
+ * the reference's nzh / indz (fftprp_utils.mod.F90:269-285) instead of nzhs / indzs.  Real-space
+ * arrays are REAL*8 (nnr1, nfields), G-space arrays COMPLEX*16 (ld, nfields), column-major.
+ *
+ *   cpb_dense_fwfft_dev   v = CMPLX(f, 0); CALL fwfftn(v,.FALSE.); g(ig) = v(nzh(ig))
+ *                         (vofrhoa_utils.mod.F90:88-95 + ppener_utils.mod.F90:91 / zgthr in
+ *                         vofrhob_utils.mod.F90:240,245; transform: fftmain_utils.mod.F90:137-153 with
+ *                         phasen, fftutil_utils.mod.F90:479-503).  nfields = 2 packs two real fields
+ *                         into one complex transform and separates them at +-G.
+ *   cpb_dense_invfft_dev  v(nzh) = g, v(indz) = CONJG(g); CALL invfftn(v,.FALSE.); f = REAL(v)
+ *                         (vofrhob_utils.mod.F90:155-173, fftmain_utils.mod.F90:105-120).  nfields = 2:
+ *                         v = g1 + i g2 at +G, conj(g1) + i conj(g2) at -G; f(:,1) = REAL(v),
+ *                         f(:,2) = AIMAG(v).  CPB_DENSE_ACCUMULATE: f += instead of f =.
+ *   cpb_vofrho_local[_dev]  the G-space electrostatics between the two: rhog = FFT(rhoe(:,1));
+ *                         ppener (ppener_utils.mod.F90:23-108): vtemp = scg*(rhog+eirop)+eivps and
+ *                         the sums eh, ei, ee, eps; v = REAL(FFT^-1(vtemp)).  Inputs scg (cppt scg),
+ *                         eivps / eirop (eicalc) have nhg entries.  ener[9] (host) = Re eh, Im eh,
+ *                         Re ei, Im ei, Re ee, Im ee, Re eps, Im eps, vploc - the caller forms
+ *                         ehep = Re(eh)*omega, epseu = 2*Re(eps)*omega ... (vofrhoa_utils.mod.F90:104-127).
+ *                         rhog / vtemp may be NULL (not returned).  v may alias rhoe, like the
+ *                         reference's rhoe (in: density, out: potential).  Exchange-correlation
+ *                         (xcener, gcener) is NOT included: the caller adds it to v.
+ */
+#define CPB_DENSE_ACCUMULATE 1u
+int cpb_dense_fwfft_dev(cpb_plan* plan, const double* f_dev, int nfields, void* g_dev, long ld, void* stream);
+int cpb_dense_invfft_dev(cpb_plan* plan, const void* g_dev, long ld, int nfields, double* f_dev,
+                         unsigned flags, void* stream);
+int cpb_vofrho_local_dev(cpb_plan* plan, const double* rhoe_dev, const double* scg_dev,
+                         const void* eivps_dev, const void* eirop_dev, void* rhog_dev, void* vtemp_dev,
+                         double* v_dev, double* ener, void* stream);
+int cpb_vofrho_local(cpb_plan* plan, const double* rhoe, const double* scg, const void* eivps,
+                     const void* eirop, void* rhog, void* vtemp, double* v, double* ener);
+
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);
 
@@ -193,7 +229,8 @@ enum {
   CPB_K_KIN = 6,
   CPB_K_SUM = 7,
   CPB_K_UNPACK = 8, /* unpack + kinetic term + occupation + c2 update */
-  CPB_NKINDS = 9
+  CPB_K_DENSE = 9,  /* dense-transform extras: real-field z passes, G gather, ppener */
+  CPB_NKINDS = 10
 };
 int cpb_plan_set_profiling(cpb_plan* plan, int on);
 /* Batches of a call alternate between `n` work spaces/streams, 1 <= n <= the number allocated at

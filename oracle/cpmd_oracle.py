@@ -441,6 +441,137 @@ def vpsi_lsd(geo: Geometry, c0, c2, f, vpot2, tpiba2, nsup, group=0, ngroups=1, 
     return c2 + c2v
 
 
+# ----------------------------------------------------------------------------------------------
+# dense transforms on the density cutoff and the local part of vofrho
+# ----------------------------------------------------------------------------------------------
+
+def make_density_geometry(nr, gcut=None, b=None) -> Geometry:
+    """Geometry of the DENSITY cutoff sphere |G|^2 < gcut = dual * gcutw (numpw_utils.mod.F90:180-184;
+    dual 4 with gcutw = (n/4)^2 gives gcut = (n/2)^2): the nhg vectors of ``loadpa`` in the same
+    sort order, whose first ngw entries are the wavefunction sphere.  The maps named nzhs/indzs in
+    the returned object are the reference's nzh/indz for this set (fftprp_utils.mod.F90:269-285),
+    ``ngw`` is nhg."""
+    if isinstance(nr, int):
+        nr = (nr, nr, nr)
+    if gcut is None:
+        gcut = (min(nr) / 2.0) ** 2
+    inyh, hg = gvectors(nr, gcut, b)
+    return fft_maps(nr, inyh, hg)
+
+
+def phasen(geo: Geometry, f):
+    """phasen (fftutil_utils.mod.F90:479-503): f(i,j,k) *= pf(MOD(k+j+i+1,2)+1), pf = (+1,-1), with
+    1-based i,j,k, i.e. (-1)^(x+y+z) in 0-based mesh coordinates.  f: padded (kr3,kr2,kr1) box."""
+    kr1, kr2, kr3 = geo.kr
+    z, y, x = np.ogrid[:kr3, :kr2, :kr1]
+    return f.reshape(kr3, kr2, kr1) * (1.0 - 2.0 * ((x + y + z) & 1))
+
+
+def fwfftn_dense(geo: Geometry, f_r):
+    """``fwfftn(v,.FALSE.)`` = fftnew(isign=+1, dense) (fftmain_utils.mod.F90:137-153): phasen, then
+    the three e^{-i...} passes with the scale 1/(n1 n2 n3) in the last one; returns ray storage
+    (read with nzh/indz)."""
+    n1, n2, n3 = geo.nr
+    box = phasen(geo, np.asarray(f_r, dtype=np.complex128))[:n3, :n2, :n1]
+    g = sfft.fftn(box, norm="forward", workers=-1)
+    return _box_to_rays(geo, g)
+
+
+def invfftn_dense(geo: Geometry, v_rays):
+    """``invfftn(v,.FALSE.)`` = fftnew(isign=-1, dense) (fftmain_utils.mod.F90:105-120): unnormalised
+    e^{+i...} passes, then phasen.  Returns the padded complex real-space array (nnr1,)."""
+    n1, n2, n3 = geo.nr
+    box = _rays_to_box(geo, v_rays)
+    r = sfft.ifftn(box, norm="forward", workers=-1)
+    out = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]), dtype=np.complex128)
+    out[:n3, :n2, :n1] = r
+    return phasen(geo, out).reshape(-1)
+
+
+def rho_to_g(geo: Geometry, rhoe):
+    """vofrhoa_utils.mod.F90:88-95 + ppener_utils.mod.F90:91: v = CMPLX(rhoe,0); fwfftn(v,.FALSE.);
+    rhog(ig) = v(nzh(ig))."""
+    return fwfftn_dense(geo, rhoe)[geo.nzhs - 1]
+
+
+def g_to_r(geo: Geometry, vg):
+    """vofrhob_utils.mod.F90:155-173: v = 0; v(indz) = CONJG(vg); v(nzh) = vg; G=0 rewritten;
+    invfftn(v,.FALSE.).  Returns the complex padded array (its real part is the potential)."""
+    v = np.zeros(geo.kr[0] * geo.nrays, dtype=np.complex128)
+    v[geo.indzs - 1] = np.conj(vg)
+    v[geo.nzhs - 1] = vg
+    if geo.geq0:
+        v[geo.nzhs[0] - 1] = vg[0]
+    return invfftn_dense(geo, v)
+
+
+def ppener(geo: Geometry, rhog, scg, eivps, eirop):
+    """ppener (ppener_utils.mod.F90:23-108).  Returns (eh, ei, ee, eps, vploc, vtemp), the four
+    sums complex like the reference's."""
+    nhg = geo.ngw
+    vtemp = np.empty(nhg, dtype=np.complex128)
+    ig1 = 0
+    eh = ei = ee = eps = 0.0 + 0.0j
+    vploc = 0.0
+    if geo.geq0:                                                       # :58-70
+        vp = eivps[0]
+        vploc = vp.real
+        eps = 0.5 * vp * np.conj(rhog[0])
+        rp = eirop[0]
+        rhet = rhog[0]
+        rg = rhet + rp
+        eh = 0.5 * scg[0] * rg.real * rg.real + 0.0j
+        ei = 0.5 * scg[0] * rp * rp
+        ee = 0.5 * scg[0] * rhet * rhet
+        vtemp[0] = scg[0] * rg
+        ig1 = 1
+    vp = eivps[ig1:]
+    rp = eirop[ig1:]
+    rhet = rhog[ig1:]
+    rg = rhet + rp                                                     # :92
+    vcg = scg[ig1:] * rg                                               # :95
+    vtemp[ig1:] = vcg + vp                                             # :96
+    eh = eh + np.sum(vcg * np.conj(rg))                                # :98
+    ei = ei + np.sum(scg[ig1:] * rp * np.conj(rp))                     # :100
+    ee = ee + np.sum(scg[ig1:] * rhet * np.conj(rhet))                 # :102
+    eps = eps + np.sum(np.conj(rhet) * vp)                             # :103
+    return eh, ei, ee, eps, vploc, vtemp
+
+
+def vofrho_local(geo: Geometry, rhoe, scg, eivps, eirop):
+    """The local (G-space electrostatic) part of vofrho: vofrhoa_utils.mod.F90:88-102 (density to G,
+    ppener) and vofrhob_utils.mod.F90:155-173 (potential back to real space), without eextern,
+    forces, stress and exchange-correlation.  Returns dict(v (nnr1,) real, rhog, vtemp, eh, ei, ee,
+    eps, vploc)."""
+    rhog = rho_to_g(geo, rhoe)
+    eh, ei, ee, eps, vploc, vtemp = ppener(geo, rhog, scg, eivps, eirop)
+    v = g_to_r(geo, vtemp)
+    return dict(v=np.ascontiguousarray(v.real), v_imag_max=float(np.abs(v.imag).max()), rhog=rhog, vtemp=vtemp,
+                eh=eh, ei=ei, ee=ee, eps=eps, vploc=vploc)
+
+
+def synthetic_vofrho_inputs(geo: Geometry, tpiba2=1.0, omega=1.0, seed=None):
+    """Synthetic G-space inputs of ppener on the density sphere: scg = 4 pi / (tpiba2 hg), 0 at G = 0
+    (the periodic Coulomb kernel), eivps / eirop = smooth random structure-factor-like complex arrays
+    (real at G = 0).  ``omega`` only scales eirop like a charge density."""
+    n = geo.nr[0]
+    if seed is None:
+        seed = 4321 + n
+    rng = np.random.default_rng(seed)
+    hg = geo.hg
+    scg = np.zeros(geo.ngw)
+    nz = hg > 1.0e-8
+    scg[nz] = 4.0 * np.pi / (tpiba2 * hg[nz])
+    gc = float(hg.max()) + 1.0
+    damp = np.exp(-hg / (0.1 * gc))
+    eivps = (rng.standard_normal(geo.ngw) + 1j * rng.standard_normal(geo.ngw)) * damp * (-0.5)
+    eirop = (rng.standard_normal(geo.ngw) + 1j * rng.standard_normal(geo.ngw)) * damp * (-0.05 / omega)
+    if geo.geq0:
+        eivps[0] = eivps[0].real
+        eirop[0] = eirop[0].real
+    return scg, eivps, eirop
+
+
 def e_test(geo: Geometry, rho_out, vpot, omega):
     """The synthetic "total energy" used for the 1e-9 Ha criterion:
     E_test = ekin + (Omega/N) * sum_r V(r) rho(r)."""

@@ -42,3 +42,30 @@ def load_golden_lsd(path):
     d["nsup"] = int(d["nsup"])
     d["nr"] = tuple(int(v) for v in d["nr"])
     return d
+
+
+def golden_vofrho_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "vofrho", "*.npz")))
+
+
+def load_golden_vofrho(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    for k in ("omega", "tpiba2"):
+        d[k] = float(d[k])
+    d["nr"] = tuple(int(v) for v in d["nr"])
+    return d
+
+
+def ener_vector(e):
+    """dict(eh, ei, ee, eps, vploc) -> the 9 doubles of the C ABI."""
+    return np.array([e["eh"].real, e["eh"].imag, e["ei"].real, e["ei"].imag, e["ee"].real, e["ee"].imag,
+                     e["eps"].real, e["eps"].imag, e["vploc"]])
+
+
+def padded_random(geo, rng):
+    """random real field on the mesh in the padded (kr3,kr2,kr1) layout, pads zero"""
+    n1, n2, n3 = geo.nr
+    a = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
+    a[:n3, :n2, :n1] = rng.random((n3, n2, n1)) - 0.3
+    return a.reshape(-1)

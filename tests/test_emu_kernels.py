@@ -307,3 +307,103 @@ def test_psi_keep_reuse(emu_cdll):
         p.rhoofr_lsd(d["c0"], d["f"], 3, ngroups=2, my_group=g, flags=lib.CPB_C0_KEEP | lib.CPB_PSI_KEEP)
         p.vpsi_lsd(d["c0"], got, d["f"], 3, v2, ngroups=2, my_group=g, flags=lib.CPB_C0_REUSE | lib.CPB_PSI_REUSE)
     assert np.array_equal(ref, got)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense transforms on the density cutoff + local part of vofrho
+# ---------------------------------------------------------------------------------------------
+from helpers import ener_vector, golden_vofrho_cases, load_golden_vofrho, padded_random  # noqa: E402
+
+
+def _dense_plan(nr, cdll, **kw):
+    geo = orc.make_density_geometry(nr)
+    return geo, Plan(geo.nr, geo.inyh, geo.hg, 1.0, 1.0, _cdll=cdll, max_batch=2, **kw)
+
+
+@pytest.mark.parametrize("nr", [16, 20, (16, 20, 24), 30, 36, 48])
+def test_vofrho_local_matches_oracle(emu_cdll, nr):
+    geo, p = _dense_plan(nr, emu_cdll)
+    nz, iz = p.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)      # nzh / indz
+    if isinstance(nr, int):
+        assert p.info["band_pruned"] == (0, 0, 0)    # the sphere fills the box; (16,20,24) prunes z
+    rho = padded_random(geo, np.random.default_rng(geo.nr[0]))
+    scg, eivps, eirop = orc.synthetic_vofrho_inputs(geo)
+    ref = orc.vofrho_local(geo, rho, scg, eivps, eirop)
+    rhog = np.empty(geo.ngw, complex)
+    vtemp = np.empty(geo.ngw, complex)
+    v, e = p.vofrho_local(rho, scg, eivps, eirop, rhog=rhog, vtemp=vtemp)
+    assert relmax(rhog, ref["rhog"]) < RTOL and relmax(vtemp, ref["vtemp"]) < RTOL
+    assert relmax(v, ref["v"]) < RTOL
+    assert np.abs(ener_vector(e) - ener_vector(ref)).max() < ETOL
+    n1, n2, n3 = geo.nr
+    v3 = v.reshape(geo.kr[2], geo.kr[1], geo.kr[0])
+    assert not v3[n3:].any() and not v3[:, n2:].any() and not v3[:, :, n1:].any()
+    # in place (v aliases rhoe like the reference's rhoe) and without the optional outputs
+    buf = rho.copy()
+    v2, e2 = p.vofrho_local(buf, scg, eivps, eirop, v=buf)
+    assert np.array_equal(v2, v) and e2 == e
+
+
+@pytest.mark.parametrize("path", golden_vofrho_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_vofrho_local_matches_golden(emu_cdll, path):
+    d = load_golden_vofrho(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=1, _cdll=emu_cdll)
+    rhog = np.empty(p.ngw, complex)
+    vtemp = np.empty(p.ngw, complex)
+    v, e = p.vofrho_local(d["rhoe"], d["scg"], d["eivps"], d["eirop"], rhog=rhog, vtemp=vtemp)
+    assert relmax(v, d["v"]) < RTOL and relmax(rhog, d["rhog"]) < RTOL and relmax(vtemp, d["vtemp"]) < RTOL
+    assert np.abs(ener_vector(e) - d["ener"]).max() < ETOL
+
+
+def test_dense_transforms_one_and_two_fields(emu_cdll):
+    """cpb_dense_fwfft_dev / cpb_dense_invfft_dev (the simulator's "device" is host memory): one
+    field, two fields packed into one transform, leading dimension > nhg, accumulate flag."""
+    geo, p = _dense_plan(20, emu_cdll)
+    rng = np.random.default_rng(3)
+    f2 = np.stack([padded_random(geo, rng), padded_random(geo, rng)])
+    ld = geo.ngw + 5
+    g2 = np.full((2, ld), 9.0 + 9.0j)
+    p.dense_fwfft_dev(f2, g2)
+    for i in range(2):
+        assert relmax(g2[i, :geo.ngw], orc.rho_to_g(geo, f2[i])) < RTOL
+    assert np.all(g2[:, geo.ngw:] == 9.0 + 9.0j)
+    g1 = np.empty(ld, complex)
+    p.dense_fwfft_dev(f2[1], g1)
+    assert relmax(g1[:geo.ngw], orc.rho_to_g(geo, f2[1])) < RTOL
+    # inverse: two fields at once == one at a time == oracle
+    back2 = np.full((2, geo.nnr1), 5.0)
+    p.dense_invfft_dev(g2, back2)
+    for i in range(2):
+        assert relmax(back2[i], orc.g_to_r(geo, g2[i, :geo.ngw]).real) < RTOL
+    back1 = np.full(geo.nnr1, 5.0)
+    p.dense_invfft_dev(g2[0], back1)
+    assert relmax(back1, back2[0]) < RTOL
+    acc = back1.copy()
+    p.dense_invfft_dev(g2[0], acc, accumulate=True)
+    assert relmax(acc, 2.0 * back1) < RTOL
+    # argument checks
+    with pytest.raises(ValueError):
+        p.dense_fwfft_dev(f2[0], np.empty(geo.ngw - 1, complex))
+    with pytest.raises(CpbError):
+        p.dense_fwfft_dev(np.empty((3, geo.nnr1)), np.empty((3, ld), complex))
+
+
+def test_density_to_potential_step(emu_cdll):
+    """rhoofr -> vofrho_local -> vpsi chained like one SCF step (rwfopt_utils.mod.F90:329 ->
+    vofrho -> forces_driver.mod.F90:224), wavefunction plan + density plan on the same mesh."""
+    n, ns = 16, 4
+    d = synthetic.make_inputs(n, ns)
+    wgeo = orc.make_geometry(n)
+    wp = _plan(d, emu_cdll, max_batch=2)
+    dgeo, dp = _dense_plan(n, emu_cdll)
+    scg, eivps, eirop = orc.synthetic_vofrho_inputs(dgeo)
+    rho, *_ = wp.rhoofr(d["c0"], d["f"])
+    v, e = dp.vofrho_local(rho, scg, eivps, eirop, v=rho)           # rho becomes V in place
+    c2 = np.zeros_like(d["c0"])
+    wp.vpsi(d["c0"], c2, d["f"], v)
+    rho_ref = orc.rhoofr(wgeo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]
+    ref = orc.vofrho_local(dgeo, rho_ref, scg, eivps, eirop)
+    c2_ref = orc.vpsi(wgeo, d["c0"], np.zeros_like(d["c0"]), d["f"], ref["v"], 1.0)
+    assert relmax(v, ref["v"]) < RTOL and relmax(c2, c2_ref) < RTOL
+    assert np.abs(ener_vector(e) - ener_vector(ref)).max() < ETOL

@@ -262,3 +262,118 @@ def test_psi_keep_reuse_device(dev):
     n0 = plan.launch_count
     plan.vpsi_dev(c0, b, d["f"], v, flags=lib.CPB_PSI_REUSE)
     assert torch.equal(a, b) and plan.launch_count - n0 < full
+
+
+# ---------------------------------------------------------------------------------------------
+# dense transforms on the density cutoff + local part of vofrho
+# ---------------------------------------------------------------------------------------------
+from helpers import ener_vector, golden_vofrho_cases, load_golden_vofrho, padded_random  # noqa: E402
+
+
+def _dense_plan(nr):
+    geo = orc.make_density_geometry(nr)
+    return geo, Plan(geo.nr, geo.inyh, geo.hg, 1.0, 1.0, max_batch=2)
+
+
+@pytest.mark.parametrize("nr", [16, 20, (16, 20, 24), 30, 48, 64, 72, 96, 120])
+def test_vofrho_local_device_and_host(dev, nr):
+    geo, p = _dense_plan(nr)
+    nz, iz = p.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)
+    rho = padded_random(geo, np.random.default_rng(geo.nr[0]))
+    scg, eivps, eirop = orc.synthetic_vofrho_inputs(geo)
+    ref = orc.vofrho_local(geo, rho, scg, eivps, eirop)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    rho_d = t(rho)
+    v_d = torch.full((p.nnr1,), 7.0, dtype=torch.float64, device=dev)
+    rhog_d = torch.empty(p.ngw, dtype=torch.complex128, device=dev)
+    vtemp_d = torch.empty_like(rhog_d)
+    e = p.vofrho_local_dev(rho_d, t(scg), t(eivps), t(eirop), v_d, rhog=rhog_d, vtemp=vtemp_d)
+    torch.cuda.synchronize()
+    assert relmax(rhog_d.cpu().numpy(), ref["rhog"]) < RTOL and relmax(vtemp_d.cpu().numpy(), ref["vtemp"]) < RTOL
+    v = v_d.cpu().numpy()
+    assert relmax(v, ref["v"]) < RTOL
+    assert np.abs(ener_vector(e) - ener_vector(ref)).max() < ETOL * max(1.0, np.abs(ener_vector(ref)).max())
+    n1, n2, n3 = geo.nr
+    v3 = v.reshape(geo.kr[2], geo.kr[1], geo.kr[0])
+    assert not v3[n3:].any() and not v3[:, n2:].any() and not v3[:, :, n1:].any()
+    # in place on the device (rho becomes V) and the host-pointer entry point: same kernels
+    e2 = p.vofrho_local_dev(rho_d, t(scg), t(eivps), t(eirop), rho_d)
+    assert torch.equal(rho_d, v_d) and e2 == e
+    v_h, e_h = p.vofrho_local(rho, scg, eivps, eirop)
+    assert np.array_equal(v_h, v) and e_h == e
+
+
+@pytest.mark.parametrize("path", golden_vofrho_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_vofrho_golden_vectors(dev, path):
+    d = load_golden_vofrho(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=1)
+    rhog = np.empty(p.ngw, complex)
+    vtemp = np.empty(p.ngw, complex)
+    v, e = p.vofrho_local(d["rhoe"], d["scg"], d["eivps"], d["eirop"], rhog=rhog, vtemp=vtemp)
+    assert relmax(v, d["v"]) < RTOL and relmax(rhog, d["rhog"]) < RTOL and relmax(vtemp, d["vtemp"]) < RTOL
+    assert np.abs(ener_vector(e) - d["ener"]).max() < ETOL
+
+
+def test_dense_transforms_two_fields_device(dev):
+    geo, p = _dense_plan(40)
+    rng = np.random.default_rng(3)
+    f2 = np.stack([padded_random(geo, rng), padded_random(geo, rng)])
+    ld = geo.ngw + 5
+    g2 = torch.full((2, ld), 9.0 + 9.0j, dtype=torch.complex128, device=dev)
+    f2_d = torch.from_numpy(f2).to(dev)
+    p.dense_fwfft_dev(f2_d, g2)
+    g2h = g2.cpu().numpy()
+    for i in range(2):
+        assert relmax(g2h[i, :geo.ngw], orc.rho_to_g(geo, f2[i])) < RTOL
+    assert np.all(g2h[:, geo.ngw:] == 9.0 + 9.0j)
+    back = torch.full((2, geo.nnr1), 5.0, dtype=torch.float64, device=dev)
+    p.dense_invfft_dev(g2, back)
+    for i in range(2):
+        assert relmax(back[i].cpu().numpy(), orc.g_to_r(geo, g2h[i, :geo.ngw]).real) < RTOL
+    one = torch.empty(geo.nnr1, dtype=torch.float64, device=dev)
+    p.dense_invfft_dev(g2[0], one)
+    assert relmax(one.cpu().numpy(), back[0].cpu().numpy()) < RTOL
+    p.dense_invfft_dev(g2[0], one, accumulate=True)
+    assert relmax(one.cpu().numpy(), 2.0 * back[0].cpu().numpy()) < RTOL
+
+
+def test_full_size_scf_step_properties(dev):
+    """North-star mesh (192^3): rhoofr -> vofrho_local -> vpsi chained on the device, checked through
+    size-independent identities: rhog(0)*omega = charge, eh = (1/2N) sum rho_tot V_H (Parseval on
+    the sphere), forward(inverse(g)) = g, and the energy identity of the hot path with the V produced
+    on the device."""
+    n, ns = 192, 8
+    d = synthetic.make_inputs(n, ns)
+    wp = Plan(d["nr"], d["inyh"], d["hg"], max_batch=4)
+    dgeo, dp = _dense_plan(n)
+    scg, eivps, eirop = orc.synthetic_vofrho_inputs(dgeo)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    c0 = t(d["c0"])
+    rho = torch.empty(wp.nnr1, dtype=torch.float64, device=dev)
+    ekin, rg, rr = wp.rhoofr_dev(c0, d["f"], rho)
+    rhog = torch.empty(dp.ngw, dtype=torch.complex128, device=dev)
+    vtemp = torch.empty_like(rhog)
+    v = torch.empty_like(rho)
+    zero = torch.zeros_like(rhog)
+    e = dp.vofrho_local_dev(rho, t(scg), zero, zero, v, rhog=rhog, vtemp=vtemp)   # pure Hartree
+    assert abs(rhog[0].real.item() - rg) < 1e-10 * rg
+    nn = float(n) ** 3
+    # rho is band limited to the density sphere except for the cube corners the sphere cuts off:
+    # use the sphere-projected density for the real-space side of Parseval
+    rho_p = torch.empty_like(rho)
+    dp.dense_invfft_dev(rhog, rho_p)
+    assert abs(e["eh"].real - 0.5 * (rho_p * v).sum().item() / nn) < ETOL * max(1.0, abs(e["eh"].real))
+    assert abs(e["ee"] - e["eh"]) < 1e-12 * abs(e["eh"]) and e["ei"] == 0 and e["eps"] == 0
+    g_back = torch.empty_like(rhog)
+    dp.dense_fwfft_dev(rho_p, g_back)
+    assert relmax(g_back.cpu().numpy(), rhog.cpu().numpy()) < RTOL
+    # full local potential, then vpsi with it: -sum dotp(c0,c2) = ekin + (1/N) sum V rho
+    dp.vofrho_local_dev(rho, t(scg), t(eivps), t(eirop), v)
+    c2 = torch.zeros_like(c0)
+    wp.vpsi_dev(c0, c2, d["f"], v)
+    w = torch.full((wp.ngw,), 2.0, dtype=torch.float64, device=dev)
+    w[0] = 1.0
+    dot = (w * (c0.real * c2.real + c0.imag * c2.imag)).sum().item()
+    e_test = ekin + (v * rho).sum().item() / nn
+    assert abs(-dot - e_test) < ETOL * max(1.0, abs(e_test))

@@ -197,3 +197,123 @@ def test_lsd_known_answers():
     rr, cs, ca = orc.lsd_finish(geo, acc, 1.0)
     assert np.abs(acc - full["rhoe"]).max() < 1e-13 * np.abs(full["rhoe"]).max()
     assert abs(cs - full["csums"]) < 1e-12 and abs(ca - full["csumsabs"]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# dense transforms + local part of vofrho: known answers from the cited formulas
+# ---------------------------------------------------------------------------------------------
+
+def _mesh_field(geo, fn):
+    n1, n2, n3 = geo.nr
+    z, y, x = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), indexing="ij")
+    a = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
+    a[:n3, :n2, :n1] = fn(x, y, z)
+    return a.reshape(-1)
+
+
+def _find_g(geo, g):
+    nh = [n // 2 + 1 for n in geo.nr]
+    m = (geo.inyh[0] == nh[0] + g[0]) & (geo.inyh[1] == nh[1] + g[1]) & (geo.inyh[2] == nh[2] + g[2])
+    idx = np.nonzero(m)[0]
+    return int(idx[0]) if idx.size else None
+
+
+def test_dense_transform_known_answers():
+    """phasen + dense fwfftn put G at inyh = nh + G (fftmain_utils.mod.F90:137-153,
+    fftutil_utils.mod.F90:479-503): a cosine has exactly two coefficients 1/2 (one in the half
+    sphere), a constant only G=0, and the inverse reproduces the field with zero imaginary part."""
+    n = 16
+    geo = orc.make_density_geometry(n)
+    assert geo.geq0 and geo.kr3min == 2 and geo.kr3max == n      # |g| <= n/2 - 1 on every axis
+    wgeo = orc.make_geometry(n)
+    assert np.array_equal(geo.inyh[:, :wgeo.ngw], wgeo.inyh)     # first ngw of nhg = wavefunction sphere
+    g = (2, -3, 1)
+    rho = _mesh_field(geo, lambda x, y, z: 0.7 + np.cos(2 * np.pi * (g[0] * x + g[1] * y + g[2] * z) / n + 0.4))
+    rg = orc.rho_to_g(geo, rho)
+    ig = _find_g(geo, g)
+    want = np.zeros(geo.ngw, complex)
+    want[0] = 0.7
+    want[ig] = 0.5 * np.exp(0.4j)
+    assert np.abs(rg - want).max() < 1e-15
+    back = orc.g_to_r(geo, rg)
+    assert np.abs(back.real - rho).max() < 1e-14 and np.abs(back.imag).max() < 1e-14
+    # pads stay zero
+    b3 = back.reshape(geo.kr[2], geo.kr[1], geo.kr[0])
+    assert not b3[n:].any() and not b3[:, n:].any() and not b3[:, :, n:].any()
+
+
+def test_density_from_rhoofr_has_nel_at_g0():
+    """rhog(G=0) * omega = number of electrons: links rhoofr's charge check
+    (rhoofr_utils.mod.F90:607-619) with the dense forward transform's 1/N scale."""
+    n, ns, omega = 16, 4, 1.7
+    geo = orc.make_geometry(n)
+    c0, f, _ = orc.synthetic_inputs(geo, ns)
+    r = orc.rhoofr(geo, c0, f, omega, 1.0)
+    dgeo = orc.make_density_geometry(n)
+    rg = orc.rho_to_g(dgeo, r["rhoe"])
+    assert abs(rg[0].real * omega - r["rsum_g"]) < 1e-12 and abs(rg[0].imag) < 1e-15
+    # |psi|^2 of functions band limited to |G| < n/4 is band limited to |G| < n/2: the density
+    # sphere holds all of it except the corners of the cube outside the sphere -> round trip is
+    # close but not exact; the part inside the sphere is reproduced exactly
+    back = orc.g_to_r(dgeo, rg).real
+    assert np.abs(orc.rho_to_g(dgeo, back) - rg).max() < 1e-15
+
+
+def test_hartree_known_answer_and_energies():
+    """ppener (ppener_utils.mod.F90:85-104) with eirop = eivps = 0 and scg = 4 pi/(tpiba2 G^2): the
+    potential of rho = a cos(G.r) is scg(G) * rho, eh = sum scg |rho_G|^2 over the half sphere =
+    (1/2N) sum_r rho(r) V(r), ee = eh, ei = eps = 0."""
+    n = 20
+    geo = orc.make_density_geometry(n)
+    g = (1, 2, -2)
+    a = 0.3
+    rho = _mesh_field(geo, lambda x, y, z: a * np.cos(2 * np.pi * (g[0] * x + g[1] * y + g[2] * z) / n))
+    scg, _, _ = orc.synthetic_vofrho_inputs(geo, tpiba2=0.9)
+    zero = np.zeros(geo.ngw, complex)
+    r = orc.vofrho_local(geo, rho, scg, zero, zero)
+    k = 4 * np.pi / (0.9 * 9.0)
+    assert np.abs(r["v"] - k * rho).max() < 1e-14
+    assert abs(r["eh"] - k * (a / 2) ** 2) < 1e-15 and abs(r["ee"] - r["eh"]) < 1e-18
+    assert r["ei"] == 0 and r["eps"] == 0 and r["vploc"] == 0
+    nn = float(n ** 3)
+    assert abs(r["eh"].real - 0.5 * np.dot(rho, r["v"]) / nn) < 1e-15
+
+
+def test_ppener_g0_special_case_and_epseu():
+    """G=0 entry (ppener_utils.mod.F90:58-70): half weights, vtemp(1) = scg(1)*rhog without vps;
+    eps = sum conj(rho_G) vps_G over the half sphere = (1/2N) sum_r rho(r) Vps(r) for real fields,
+    so that epseu = 2 Re(eps) omega is the integral of rho * Vps (vofrhoa_utils.mod.F90:127)."""
+    n = 16
+    geo = orc.make_density_geometry(n)
+    rng = np.random.default_rng(5)
+    scg, eivps, eirop = orc.synthetic_vofrho_inputs(geo, seed=9)
+    scg = scg.copy()
+    scg[0] = 0.37                                            # exercise the G=0 formulas
+    rhog = orc.rho_to_g(geo, orc.g_to_r(geo, (rng.standard_normal(geo.ngw) + 1j * rng.standard_normal(geo.ngw)
+                                              ) * np.exp(-geo.hg / 20)).real)
+    eh, ei, ee, eps, vploc, vtemp = orc.ppener(geo, rhog, scg, eivps, eirop)
+    assert vploc == eivps[0].real
+    assert vtemp[0] == scg[0] * (rhog[0] + eirop[0])
+    assert np.abs(vtemp[1:] - (scg[1:] * (rhog[1:] + eirop[1:]) + eivps[1:])).max() == 0
+    # real-space cross-check of eps: Vps(r) from the same scatter/inverse as the potential
+    rho_r = orc.g_to_r(geo, rhog).real
+    vps_r = orc.g_to_r(geo, eivps).real
+    nn = float(n ** 3)
+    assert abs(eps.real - 0.5 * np.dot(rho_r, vps_r) / nn) < 1e-13
+    # Hartree energy of the total (electron + Gaussian ion) charge, with the G=0 half weight
+    tot = rhog + eirop
+    want = 0.5 * scg[0] * tot[0].real ** 2 + np.sum(scg[1:] * np.abs(tot[1:]) ** 2)
+    assert abs(eh - want) < 1e-13
+
+
+def test_vofrho_golden_vectors_frozen():
+    from helpers import golden_vofrho_cases, load_golden_vofrho
+    cases = golden_vofrho_cases()
+    assert cases
+    for path in cases:
+        d = load_golden_vofrho(path)
+        geo = orc.fft_maps(d["nr"], d["inyh"], d["hg"])
+        assert np.array_equal(geo.nzhs, d["nzh"]) and np.array_equal(geo.indzs, d["indz"])
+        r = orc.vofrho_local(geo, d["rhoe"], d["scg"], d["eivps"], d["eirop"])
+        assert np.abs(r["v"] - d["v"]).max() <= 1e-13 * np.abs(d["v"]).max()
+        assert np.abs(r["rhog"] - d["rhog"]).max() <= 1e-14

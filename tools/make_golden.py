@@ -26,6 +26,12 @@ CASES = [
     ("n16_s7_grp1of3", (16, 16, 16), 7, "mixed", 1.0, 1.0, (1, 3)),
 ]
 
+VOFRHO_CASES = [
+    # name, mesh, omega, tpiba2
+    ("n16", (16, 16, 16), 1.3, 0.9),
+    ("n16x20x24", (16, 20, 24), 2.0, 1.1),
+]
+
 LSD_CASES = [
     # name, mesh, nstate, nsup, omega, tpiba2
     ("n16_s7_nsup3", (16, 16, 16), 7, 3, 1.3, 0.9),
@@ -61,6 +67,21 @@ def main():
                             ekin=rho["ekin"], rsum_g=rho["rsum_g"], rsum_r=rho["rsum_r"], csums=rho["csums"],
                             csumsabs=rho["csumsabs"], c2_in=c2_in, c2_out=c2)
         print("lsd/" + name, "ngw", geo.ngw)
+    # local part of vofrho on the density cutoff (tests/golden/vofrho/): the density comes from rhoofr
+    os.makedirs(os.path.join(out, "vofrho"), exist_ok=True)
+    for name, nr, omega, tpiba2 in VOFRHO_CASES:
+        geo = orc.make_geometry(nr)
+        c0, f, _ = orc.synthetic_inputs(geo, 4, seed=99 + nr[0], f_pattern="all2")
+        rhoe = orc.rhoofr(geo, c0, f, omega, tpiba2)["rhoe"]
+        dgeo = orc.make_density_geometry(nr)
+        scg, eivps, eirop = orc.synthetic_vofrho_inputs(dgeo, tpiba2, omega, seed=31 + nr[2])
+        r = orc.vofrho_local(dgeo, rhoe, scg, eivps, eirop)
+        ener = np.array([r["eh"].real, r["eh"].imag, r["ei"].real, r["ei"].imag, r["ee"].real, r["ee"].imag,
+                         r["eps"].real, r["eps"].imag, r["vploc"]])
+        np.savez_compressed(os.path.join(out, "vofrho", name + ".npz"), nr=np.array(nr), inyh=dgeo.inyh, hg=dgeo.hg,
+                            nzh=dgeo.nzhs, indz=dgeo.indzs, omega=omega, tpiba2=tpiba2, rhoe=rhoe, scg=scg,
+                            eivps=eivps, eirop=eirop, rhog=r["rhog"], vtemp=r["vtemp"], v=r["v"], ener=ener)
+        print("vofrho/" + name, "nhg", dgeo.ngw)
 
 
 if __name__ == "__main__":
