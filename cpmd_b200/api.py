@@ -271,6 +271,36 @@ class Plan:
         self._check(rc)
         return c2
 
+    # -- k-points (tkpts%tkpnt): c0/c2 (nstate, ld >= 2 ngw) CUDA tensors, one k-point per call ------
+    def _kpt_args(self, c0, nstate):
+        ns, ld = c0.shape
+        if nstate is None:
+            nstate = ns
+        if nstate > ns or ld < 2 * self.ngw:
+            raise ValueError("k-point c0 must be (nstate, ld >= 2*ngw)")
+        return int(nstate), int(ld)
+
+    def rhoofr_kpt_dev(self, c0, f, wk, hgkp, hgkm, rhoe, nstate=None, ngroups=1, my_group=0, accumulate=False,
+                       stream=None):
+        """``cpb_rhoofr_kpt_dev``: one k-point of rhoofr_c (rhoofr_c_utils.mod.F90:117-178).
+        Returns (ekin, rsum_g, rsum_r) contributions."""
+        nstate, ld = self._kpt_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = [C.c_double() for _ in range(3)]
+        flags = _lib.CPB_RHO_ACCUMULATE if accumulate else 0
+        self._check(self._L.cpb_rhoofr_kpt_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, float(wk), _ptr(hgkp),
+                                               _ptr(hgkm), ngroups, my_group, _ptr(rhoe),
+                                               *[C.byref(o) for o in out], flags, _stream_ptr(stream)))
+        return tuple(o.value for o in out)
+
+    def vpsi_kpt_dev(self, c0, c2, f, hgkp, hgkm, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
+        """``cpb_vpsi_kpt_dev``: vpsi's k-point branch for one k-point (vpsi_utils.mod.F90:562-625)."""
+        nstate, ld = self._kpt_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        self._check(self._L.cpb_vpsi_kpt_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, _ptr(hgkp),
+                                             _ptr(hgkm), _ptr(vpot), ngroups, my_group, flags, _stream_ptr(stream)))
+        return c2
+
     # -- dense transforms on the density cutoff + local part of vofrho (plan built from nhg) --------
     # Arrays follow the package convention: Fortran (ld, nfields) = C-order (nfields, ld).
     def _dense_shapes(self, f, g):

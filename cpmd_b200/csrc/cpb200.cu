@@ -117,6 +117,11 @@ struct cpb_plan {
   std::vector<int32_t> nzhs, indzs;
   // device data
   PlanDev pd;
+  // k-points: same plan data with the k-point gather table; set for the duration of a *_kpt call
+  PlanDev pdk;
+  uint32_t* d_gtab_k = nullptr;
+  bool kpt_mode = false;
+  const double *kpt_hgkp = nullptr, *kpt_hgkm = nullptr;
   int *d_ylo = nullptr, *d_yhi = nullptr, *d_rayoff = nullptr;
   uint32_t *d_gpos = nullptr, *d_gneg = nullptr, *d_gtab = nullptr;
   double* d_hg = nullptr;
@@ -187,6 +192,7 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_gpos);
   rt::dfree(p->d_gneg);
   rt::dfree(p->d_gtab);
+  rt::dfree(p->d_gtab_k);
   rt::dfree(p->d_hg);
   rt::dfree(p->d_tw1);
   rt::dfree(p->d_tw2);
@@ -388,8 +394,8 @@ int ew_ppg(const cpb_plan* p, int npair, int waves) {
 void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb) {
   cudaStream_t st = w.s;
   Timed t(p, st, CPB_K_X_INV);
-  p->kx->x_inv(st, c0, ldc, w.T1, p->pd, prb, nb, pairs_per_group(p, nb, p->nrp / p->kx->sl, p->kx->x_inv_blocks),
-               p->half_x);
+  p->kx->x_inv(st, c0, ldc, w.T1, p->kpt_mode ? p->pdk : p->pd, prb, nb,
+               pairs_per_group(p, nb, p->nrp / p->kx->sl, p->kx->x_inv_blocks), p->half_x);
 }
 
 // x pass, forward, in sub-batches of x_sub pairs: k_x_fwd writes the sub-batch's band-ray storage
@@ -408,7 +414,17 @@ void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, lo
     Timed t(p, st, CPB_K_UNPACK);
     const int ppg = ew_ppg(p, ns, 8);
     const dim3 grid((p->ngw + 255) / 256, (ns + ppg - 1) / ppg);
-    if (accumulate) {
+    if (p->kpt_mode) {
+      if (accumulate) {
+        auto k = k_unpack_kpt<true>;
+        CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)w.G, c0, c2, ldc, p->pd, prs, p->kpt_hgkp, p->kpt_hgkm,
+                   p->geq0, ns, ppg);
+      } else {
+        auto k = k_unpack_kpt<false>;
+        CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)w.G, c0, c2, ldc, p->pd, prs, p->kpt_hgkp, p->kpt_hgkm,
+                   p->geq0, ns, ppg);
+      }
+    } else if (accumulate) {
       auto k = k_unpack<true>;
       CPB_LAUNCH(k, grid, dim3(256), 0, st, (const cplx*)w.G, c0, c2, ldc, p->pd, prs, ns, ppg);
     } else {
@@ -774,7 +790,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     const int nrp = (nrays + SL - 1) / SL * SL;
     if ((double)nxb * nrp > 4.0e9) throw Error(CPB_ERR_UNSUPPORTED, "band-ray storage exceeds 32-bit positions");
     std::vector<uint32_t> gpos(ngw), gneg(ngw), gtab((size_t)nxb * nrp, kNoPW);
-    if ((unsigned)ngw >= kNegPW) throw Error(CPB_ERR_UNSUPPORTED, "ngw too large");
+    if (2.0 * ngw >= (double)kNegPW) throw Error(CPB_ERR_UNSUPPORTED, "ngw too large");
     {
       std::vector<unsigned char> occ((size_t)nrays * n1, 0);
       for (int i = 0; i < ngw; ++i) {
@@ -832,6 +848,13 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->d_gpos = upload(gpos);
     p->d_gneg = upload(gneg);
     p->d_gtab = upload(gtab);
+    {
+      // k-point gather table: the -G position of plane wave ig takes c0(ig + ngw), unconjugated
+      std::vector<uint32_t> gtab_k(gtab);
+      for (int i = 0; i < ngw; ++i)
+        if (gneg[i] != gpos[i]) gtab_k[gneg[i]] = (uint32_t)i + (uint32_t)ngw;
+      p->d_gtab_k = upload(gtab_k);
+    }
     p->d_hg = upload(std::vector<double>(hg, hg + ngw));
     p->d_tw1 = upload(make_twiddles(n1));
     p->d_tw2 = upload(make_twiddles(n2));
@@ -902,6 +925,8 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     pd.tw3 = p->d_tw3;
     pd.tpiba2 = tpiba2;
     pd.inv_n = 1.0 / ((double)n1 * n2 * n3);
+    p->pdk = pd;
+    p->pdk.gtab = p->d_gtab_k;
     *out = p;
     return CPB_OK;
   } catch (const Error& e) {
@@ -1283,6 +1308,138 @@ int cpb_vofrho_local(cpb_plan* p, const double* rhoe, const double* scg, const v
     return CPB_OK;
   } catch (const Error& e) {
     return fail(e.code, e.what());
+  }
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// k-points (tkpts%tkpnt), one k-point per call: rhoofr_c's inner loops and vpsi's k-branch
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct KptScope {  // the plan is not re-entrant: the mode lives for the duration of one call
+  cpb_plan* p;
+  KptScope(cpb_plan* p_, const double* hgkp, const double* hgkm) : p(p_) {
+    p->kpt_mode = true;
+    p->kpt_hgkp = hgkp;
+    p->kpt_hgkm = hgkm;
+    p->psi_valid = false;
+  }
+  ~KptScope() {
+    p->kpt_mode = false;
+    p->kpt_hgkp = p->kpt_hgkm = nullptr;
+  }
+};
+
+// every state of the group's block is its own transform (njump = 1, vpsi_utils.mod.F90:237-238)
+std::vector<PairHost> block_singles(int nstate, int my_group, int ngroups) {
+  std::vector<PairHost> out;
+  const int nblk = nbr_el_in_blk(nstate, my_group, ngroups);
+  for (int i = 1; i <= nblk; ++i) {
+    PairHost q;
+    q.s1 = get_el_in_blk(i, nstate, my_group, ngroups) - 1;
+    q.s2 = -1;
+    out.push_back(q);
+  }
+  return out;
+}
+
+int check_kpt(cpb_plan* p, const void* c0, long ld, int nstate, const double* f, const double* hgkp,
+              const double* hgkm, int ngroups, int my_group) {
+  if (int e = check_common(p, c0, ld, nstate, f, ngroups, my_group)) return e;
+  if (ld < 2L * p->ngw) return fail(CPB_ERR_INVALID, "k-points: leading dimension smaller than ngwk = 2*ngw");
+  if (!hgkp || !hgkm) return fail(CPB_ERR_INVALID, "null hgkp / hgkm");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb_rhoofr_kpt_dev(cpb_plan* p, const void* c0_dev, long ld, int nstate, const double* f, double wk,
+                       const double* hgkp_dev, const double* hgkm_dev, int ngroups, int my_group, double* rhoe_dev,
+                       double* ekin, double* rsum_g, double* rsum_r, unsigned flags, void* stream) {
+  if (int e = check_kpt(p, c0_dev, ld, nstate, f, hgkp_dev, hgkm_dev, ngroups, my_group)) return e;
+  if (!rhoe_dev) return fail(CPB_ERR_INVALID, "null rhoe");
+  try {
+    rt::set_device(p->device);
+    KptScope scope(p, hgkp_dev, hgkm_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cplx* c0 = (const cplx*)c0_dev;
+    const int nblk = nbr_el_in_blk(nstate, my_group, ngroups);
+    const int first = nblk > 0 ? get_el_in_blk(1, nstate, my_group, ngroups) - 1 : 0;
+    std::vector<PairHost> pairs;
+    std::vector<double> ca, cb;
+    for (const PairHost& q : block_singles(nstate, my_group, ngroups)) {
+      if (f[q.s1] == 0.0) continue;                      // rhoofr_c_utils.mod.F90:145
+      pairs.push_back(q);
+      ca.push_back(wk * f[q.s1] / p->omega);             // :165, build_density_sum(coef3, coef3, ...)
+      cb.push_back(wk * f[q.s1] / p->omega);
+    }
+    ensure_red(p, kRedPerState * nblk + 3 * kSumBlocks);
+    if (!(flags & CPB_RHO_ACCUMULATE)) rt::dzero(rhoe_dev, p->nnr1() * sizeof(double), st);   // :107
+    if (nblk > 0) {
+      auto k = k_kin_energy_kpt;                                                               // :117-140
+      Timed t(p, st, CPB_K_KIN);
+      CPB_LAUNCH(k, dim3(kKinChunks, nblk), dim3(256), 2 * 256 * sizeof(double), st, c0, ld, first, p->ngw, hgkp_dev,
+                 hgkm_dev, p->d_red);
+    }
+    run_rhoofr(p, c0, ld, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), (int)pairs.size(), rhoe_dev,
+               rhoe_dev, nullptr, st, nullptr);
+    launch_sum(p, rhoe_dev, p->nnr1(), p->d_red + kRedPerState * nblk, st);
+    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + kSumBlocks) * sizeof(double), st);
+    rt::sync(st);
+    resolve_spans(p);
+    double xkin = 0.0, rsum = 0.0;
+    for (int i = 0; i < nblk; ++i) {
+      const double fi = f[first + i];
+      if (fi == 0.0) continue;                            // :118
+      double sk = 0.0, sd = 0.0;
+      for (int c = 0; c < kKinChunks; ++c) {
+        sk += p->h_red[(size_t)kRedPerState * i + 2 * c];
+        sd += p->h_red[(size_t)kRedPerState * i + 2 * c + 1];
+      }
+      rsum += wk * fi * sd;                               // :119
+      xkin += 0.5 * wk * fi * sk;                         // :138
+    }
+    double sr = 0.0;
+    for (int i = 0; i < kSumBlocks; ++i) sr += p->h_red[(size_t)kRedPerState * nblk + i];
+    if (ekin) *ekin = xkin * p->tpiba2;                   // :182
+    if (rsum_g) *rsum_g = rsum;
+    if (rsum_r) *rsum_r = sr * p->omega / ((double)p->nr[0] * p->nr[1] * p->nr[2]);   // :260-261, of rhoe so far
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+int cpb_vpsi_kpt_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                     const double* hgkp_dev, const double* hgkm_dev, const double* vpot_dev, int ngroups,
+                     int my_group, unsigned flags, void* stream) {
+  if (int e = check_kpt(p, c0_dev, ld, nstate, f, hgkp_dev, hgkm_dev, ngroups, my_group)) return e;
+  if (!c2_dev || !vpot_dev) return fail(CPB_ERR_INVALID, "null c2 or vpot");
+  try {
+    rt::set_device(p->device);
+    KptScope scope(p, hgkp_dev, hgkm_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::vector<PairHost> pairs = block_singles(nstate, my_group, ngroups);
+    std::vector<double> fi(pairs.size()), unused(pairs.size(), 0.0);
+    for (size_t i = 0; i < pairs.size(); ++i) {
+      fi[i] = f[pairs[i].s1];
+      if (fi[i] == 0.0) fi[i] = 2.0;                      // vpsi_utils.mod.F90:563-564
+    }
+    run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, unused, st), (int)pairs.size(),
+             (int)pairs.size(), vpot_dev, vpot_dev, !(flags & CPB_VPSI_OVERWRITE), nullptr, st, nullptr);
+    rt::sync(st);
+    resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
   }
 }
 

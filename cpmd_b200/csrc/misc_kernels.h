@@ -219,4 +219,79 @@ CPB_GLOBAL k_ppener(const cplx* CPB_RESTRICT rhog, const double* CPB_RESTRICT sc
   if (tid < 8) partial[(size_t)tid * gridDim.x + blockIdx.x] = red[tid * 256];
 }
 
+// ---------------------------------------------------------------------------------------------
+// k-points (tkpts%tkpnt): one complex state per transform, c0(2 ngw, nstate) = +G components, then
+// -G components.  The gather of k_x_inv runs unchanged on a second position table (gtab_k: the -G
+// positions hold ig + ngw without the conjugation flag = set_psi_1_state_g_kpts,
+// state_utils.mod.F90:192-224); these are the two G-space kernels that differ.
+// ---------------------------------------------------------------------------------------------
+// kinetic energy and norm of rhoofr_c (rhoofr_c_utils.mod.F90:117-140): out[(st*kKinChunks+c)*2] =
+// sum_G hgkp |c(G)|^2 + hgkm |c(G+ngw)|^2, out[.. + 1] = sum over all 2 ngw components |c|^2
+CPB_GLOBAL k_kin_energy_kpt(const cplx* CPB_RESTRICT c0, long ldc, int first_state, int ngw,
+                            const double* CPB_RESTRICT hgkp, const double* CPB_RESTRICT hgkm,
+                            double* CPB_RESTRICT out) {
+  CPB_DYN_SMEM(double, red);  // 2*256
+  const int tid = threadIdx.x;
+  const int st = blockIdx.y;
+  const int per = (ngw + kKinChunks - 1) / kKinChunks;
+  const int g0 = blockIdx.x * per;
+  const int g1 = (g0 + per < ngw) ? g0 + per : ngw;
+  const cplx* c = c0 + (size_t)(first_state + st) * ldc;
+  double sk = 0.0, sd = 0.0;
+  for (int ig = g0 + tid; ig < g1; ig += 256) {
+    const cplx a = c[ig], b = c[ig + ngw];
+    const double ma = a.x * a.x + a.y * a.y, mb = b.x * b.x + b.y * b.y;
+    sk += hgkp[ig] * ma + hgkm[ig] * mb;
+    sd += ma + mb;
+  }
+  red[tid] = sk;
+  red[256 + tid] = sd;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+      red[tid] += red[tid + s];
+      red[256 + tid] += red[256 + tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[((size_t)st * kKinChunks + blockIdx.x) * 2] = red[0];
+    out[((size_t)st * kKinChunks + blockIdx.x) * 2 + 1] = red[256];
+  }
+}
+
+// vpsi_utils.mod.F90:614-625 + add_wfn (:717): C2(ig) = -fi (tpiba2/2 hgkp c0(ig) + psi(nzhs(ig))),
+// C2(ig+ngw) = -fi (tpiba2/2 hgkm c0(ig+ngw) + psi(indzs(ig))), C2(1+ngw) = 0 if geq0.
+// pr.st1 = state, pr.ca = fi.  grid = (ceil(ngw/256), pair groups), block = 256
+template <bool ACC>
+CPB_GLOBAL k_unpack_kpt(const cplx* CPB_RESTRICT G, const cplx* CPB_RESTRICT c0, cplx* CPB_RESTRICT c2, long ldc,
+                        PlanDev pd, PairDev pr, const double* CPB_RESTRICT hgkp, const double* CPB_RESTRICT hgkm,
+                        int geq0, int npair, int ppg) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  const uint32_t lp = pd.gpos[ig], lm = pd.gneg[ig];
+  const double kp = 0.5 * pd.tpiba2 * hgkp[ig], km = 0.5 * pd.tpiba2 * hgkm[ig];
+  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
+  const bool zero_m = geq0 && ig == 0;
+  for (int pair = p0; pair < p1; ++pair) {
+    const int s1 = pr.st1[pair];
+    const double fi = pr.ca[pair];
+    const cplx* g = G + (size_t)pair * g_pair;
+    const cplx fp = g[lp], fm = g[lm];
+    const cplx a = c0[(size_t)s1 * ldc + ig], b = c0[(size_t)s1 * ldc + ig + pd.ngw];
+    cplx* o1 = c2 + (size_t)s1 * ldc + ig;
+    cplx* o2 = o1 + pd.ngw;
+    cplx r1 = mk(-fi * (kp * a.x + fp.x), -fi * (kp * a.y + fp.y));
+    cplx r2 = zero_m ? mk(0.0, 0.0) : mk(-fi * (km * b.x + fm.x), -fi * (km * b.y + fm.y));
+    if (ACC) {
+      r1 = cadd(r1, *o1);
+      r2 = cadd(r2, *o2);
+    }
+    *o1 = r1;
+    *o2 = r2;
+  }
+}
+
 }  // namespace cpb

@@ -22,6 +22,7 @@ CPB_ERR_CHARGE = -5
 CPB_VPSI_OVERWRITE = 1
 CPB_VPSI_TKSHAM = 2
 CPB_RHO_CHECK_CHARGE = 1
+CPB_RHO_ACCUMULATE = 2
 CPB_C0_KEEP = 0x10
 CPB_C0_REUSE = 0x20
 CPB_PSI_KEEP = 0x40
@@ -91,6 +92,11 @@ SYMBOLS = {
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "cpb_vofrho_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "cpb_rhoofr_kpt_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
+    "cpb_vpsi_kpt_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),

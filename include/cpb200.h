@@ -62,6 +62,7 @@ typedef enum {
 #define CPB_VPSI_OVERWRITE 1u /* c2 = result instead of the reference's c2 += result */
 #define CPB_VPSI_TKSHAM 2u    /* cntl%tksham: f==0 -> fi=0.5 instead of 1 (vpsi_utils:628-633) */
 #define CPB_RHO_CHECK_CHARGE 1u /* return CPB_ERR_CHARGE like the reference's stopgm */
+#define CPB_RHO_ACCUMULATE 2u   /* cpb_rhoofr_kpt*: add to rhoe instead of zeroing it first (k-points after the first) */
 /* host-pointer entry points only: device-side cache of the group's c0 block */
 #define CPB_C0_KEEP 0x10u  /* after this call the uploaded block stays valid on the device */
 #define CPB_C0_REUSE 0x20u /* skip the upload if (c0 pointer, ld, nstate, group) match the kept block */
@@ -211,6 +212,32 @@ int cpb_vofrho_local_dev(cpb_plan* plan, const double* rhoe_dev, const double* s
                          double* v_dev, double* ener, void* stream);
 int cpb_vofrho_local(cpb_plan* plan, const double* rhoe, const double* scg, const void* eivps,
                      const void* eirop, void* rhog, void* vtemp, double* v, double* ener);
+
+/* ---- k-points (tkpts%tkpnt) ------------------------------------------------------------------
+ * Complex states, one per transform (njump = 1, vpsi_utils.mod.F90:237-238).  One k-point per call,
+ * the caller keeps the reference's loops over k-point blocks (rhoofr_c_utils.mod.F90:112-116; vpsi's
+ * ikind argument).  c0/c2 are (ld >= nkpt%ngwk = 2*ngw, nstate): components 1..ngw belong to +G,
+ * ngw+1..2*ngw to -G (set_psi_1_state_g_kpts, state_utils.mod.F90:192-224).  hgkp/hgkm: |k+G|^2,
+ * |k-G|^2 of this k-point, ngw doubles each (kpts hgkp(:,ikind), hgkm(:,ikind)).
+ *   cpb_rhoofr_kpt_dev  one ikind iteration of rhoofr_c (rhoofr_c_utils.mod.F90:117-178): rhoe +=
+ *                       wk f_i / omega |psi_i(r)|^2 over the group's block; f = crge%f(:,ikk), wk =
+ *                       wk(ikk).  Without CPB_RHO_ACCUMULATE rhoe is zeroed first (:107, first k-point).
+ *                       ekin / rsum_g: this k-point's (and block's) contribution to ener_com%ekin
+ *                       (:138,182) and chrg%csumg (:119); rsum_r: integral of rhoe as it stands.
+ *   cpb_vpsi_kpt_dev    vpsi with tkpts%tkpnt for k-point ikind (vpsi_utils.mod.F90:432,487-493,
+ *                       562-564,614-625): fi = f (2 if zero), c2(ig) += -fi (tpiba2/2 hgkp c0(ig) +
+ *                       FFT[V psi](+G)), c2(ig+ngw) += -fi (tpiba2/2 hgkm c0(ig+ngw) + FFT[V psi](-G)),
+ *                       the -G slot of G=0 is left alone (zeroed with CPB_VPSI_OVERWRITE).
+ * Not covered (the shim takes the original path): k-points with cntl%tlsd (the reference applies the
+ * Gamma-only mixed-pair formula to state nsup, vpsi_utils.mod.F90:451-469), tgaugep/tgaugef, tkblock
+ * swapping (the caller's job), Vanderbilt, symrho. */
+int cpb_rhoofr_kpt_dev(cpb_plan* plan, const void* c0_dev, long ld, int nstate, const double* f, double wk,
+                       const double* hgkp_dev, const double* hgkm_dev, int ngroups, int my_group,
+                       double* rhoe_dev, double* ekin, double* rsum_g, double* rsum_r, unsigned flags,
+                       void* stream);
+int cpb_vpsi_kpt_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                     const double* hgkp_dev, const double* hgkm_dev, const double* vpot_dev, int ngroups,
+                     int my_group, unsigned flags, void* stream);
 
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);

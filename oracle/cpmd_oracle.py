@@ -572,6 +572,104 @@ def synthetic_vofrho_inputs(geo: Geometry, tpiba2=1.0, omega=1.0, seed=None):
     return scg, eivps, eirop
 
 
+# ----------------------------------------------------------------------------------------------
+# k-points (tkpts%tkpnt): complex states, one per transform, c0(ngwk = 2 ngw, nstate) per k-point:
+# +G components first, then the -G components
+# ----------------------------------------------------------------------------------------------
+
+def set_psi_1_state_g_kpts(geo: Geometry, c1, alpha=1.0):
+    """state_utils.mod.F90:192-224: psi(nzhs) = c1(1:ngw), psi(indzs) = c1(ngw+1:2ngw), G=0 last."""
+    ngw = geo.ngw
+    psi = np.zeros(geo.kr[0] * geo.nrays, dtype=np.complex128)
+    psi[geo.nzhs - 1] = alpha * c1[:ngw]
+    psi[geo.indzs - 1] = alpha * c1[ngw:2 * ngw]
+    if geo.geq0:
+        psi[geo.nzhs[0] - 1] = alpha * c1[0]
+    return psi
+
+
+def rhoofr_kpt(geo: Geometry, c0, f, wk, hgkp, hgkm, omega, tpiba2, group=0, ngroups=1, rhoe=None):
+    """One k-point of ``rhoofr_c`` (rhoofr_c_utils.mod.F90:112-180): c0 (nstate, 2 ngw), f = crge%f(:,ikk),
+    wk = wk(ikk), hgkp/hgkm = |k+G|^2, |k-G|^2 (ngw each).  ``rhoe`` (nnr1,) is accumulated into if
+    given (the reference zeroes it once before the k-point loop, :107).  Returns dict(rhoe, ekin,
+    rsum_g) with this k-point's contributions to ener_com%ekin (:138,182) and chrg%csumg (:119)."""
+    nstate = c0.shape[0]
+    ngw = geo.ngw
+    rsum = 0.0
+    xkin = 0.0
+    for i in range(nstate):                                                    # :117-140
+        if f[i] != 0.0:
+            rsum += wk * f[i] * float(np.sum(c0[i].real ** 2 + c0[i].imag ** 2))
+            sk1 = float(np.sum(hgkp * np.abs(c0[i, :ngw]) ** 2 + hgkm * np.abs(c0[i, ngw:2 * ngw]) ** 2))
+            xkin += 0.5 * wk * f[i] * sk1
+    if rhoe is None:
+        rhoe = np.zeros(geo.nnr1, dtype=np.float64)
+    nblk = part_1d_nbr_el_in_blk(nstate, group, ngroups)
+    for i in range(1, nblk + 1):                                               # :143-178
+        is1 = part_1d_get_el_in_blk(i, nstate, group, ngroups) - 1
+        if f[is1] == 0.0:
+            continue
+        psi = invfftn_sparse(geo, set_psi_1_state_g_kpts(geo, c0[is1]))        # :150-154
+        coef3 = wk * f[is1] / omega                                            # :165
+        rhoe += coef3 * psi.real ** 2 + coef3 * psi.imag ** 2                  # :173
+    return dict(rhoe=rhoe, ekin=xkin * tpiba2, rsum_g=rsum)
+
+
+def vpsi_kpt(geo: Geometry, c0, c2, f, hgkp, hgkm, vpot, tpiba2, group=0, ngroups=1):
+    """``vpsi`` with tkpts%tkpnt for one k-point (vpsi_utils.mod.F90:238,377,432,487-493,562-564,
+    614-625): njump = 1, fi = f (2 if zero), C2(ig) = -fi (tpiba2/2 hgkp c0(ig) + psi(nzhs)),
+    C2(ig+ngw) = -fi (tpiba2/2 hgkm c0(ig+ngw) + psi(indzs)), C2(1+ngw) = 0 if geq0; c2 += C2."""
+    nstate = c0.shape[0]
+    ngw = geo.ngw
+    c2v = np.zeros_like(c2)
+    nblk = part_1d_nbr_el_in_blk(nstate, group, ngroups)
+    for i in range(1, nblk + 1):
+        is1 = part_1d_get_el_in_blk(i, nstate, group, ngroups) - 1
+        psi = invfftn_sparse(geo, set_psi_1_state_g_kpts(geo, c0[is1]))
+        psi = fwfftn_sparse(geo, vpot * psi)
+        fi = f[is1]
+        if fi == 0.0:
+            fi = 2.0                                                           # :563-564
+        fp = psi[geo.nzhs - 1]
+        fm = psi[geo.indzs - 1]
+        c2v[is1, :ngw] = -fi * (0.5 * tpiba2 * hgkp * c0[is1, :ngw] + fp)      # :619-620
+        c2v[is1, ngw:2 * ngw] = -fi * (0.5 * tpiba2 * hgkm * c0[is1, ngw:2 * ngw] + fm)   # :621-622
+        if geo.geq0:
+            c2v[is1, ngw] = 0.0                                                # :625
+    return c2 + c2v
+
+
+def synthetic_kpt_inputs(geo: Geometry, nstate, kvec=(0.25, 0.1, -0.3), seed=None):
+    """Complex k-point states c0 (nstate, 2 ngw) (c0[ngw] = 0 where geq0: the -G slot of G=0 is
+    unused), hgkp/hgkm for k = kvec (units of 2 pi/alat, cubic cell), occupations and a potential."""
+    n = geo.nr[0]
+    if seed is None:
+        seed = 2468 + n + 7 * nstate
+    rng = np.random.default_rng(seed)
+    ngw = geo.ngw
+    nh = np.array([v // 2 + 1 for v in geo.nr])
+    g = (geo.inyh - nh[:, None]).astype(np.float64)
+    k = np.asarray(kvec, dtype=np.float64)[:, None]
+    hgkp = ((g + k) ** 2).sum(axis=0)
+    hgkm = ((g - k) ** 2).sum(axis=0)
+    gcutw = (min(geo.nr) / 4.0) ** 2
+    c0 = np.empty((nstate, 2 * ngw), dtype=np.complex128)
+    for i in range(nstate):
+        c = rng.standard_normal(2 * ngw) + 1j * rng.standard_normal(2 * ngw)
+        c *= np.exp(-np.concatenate([hgkp, hgkm]) / (0.25 * gcutw))
+        if geo.geq0:
+            c[ngw] = 0.0
+        c /= np.sqrt(np.sum(np.abs(c) ** 2))
+        c0[i] = c
+    f = np.full(nstate, 2.0)
+    f[1::4] = 0.0
+    f[2::5] = 1.0
+    n1, n2, n3 = geo.nr
+    v = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
+    v[:n3, :n2, :n1] = -rng.random((n3, n2, n1))
+    return c0, f, hgkp, hgkm, v.reshape(-1)
+
+
 def e_test(geo: Geometry, rho_out, vpot, omega):
     """The synthetic "total energy" used for the 1e-9 Ha criterion:
     E_test = ekin + (Omega/N) * sum_r V(r) rho(r)."""

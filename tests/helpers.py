@@ -69,3 +69,16 @@ def padded_random(geo, rng):
     a = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
     a[:n3, :n2, :n1] = rng.random((n3, n2, n1)) - 0.3
     return a.reshape(-1)
+
+
+def golden_kpt_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "kpt", "*.npz")))
+
+
+def load_golden_kpt(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    for k in ("omega", "tpiba2", "wk", "ekin", "rsum_g"):
+        d[k] = float(d[k])
+    d["nr"] = tuple(int(v) for v in d["nr"])
+    return d

@@ -407,3 +407,78 @@ def test_density_to_potential_step(emu_cdll):
     c2_ref = orc.vpsi(wgeo, d["c0"], np.zeros_like(d["c0"]), d["f"], ref["v"], 1.0)
     assert relmax(v, ref["v"]) < RTOL and relmax(c2, c2_ref) < RTOL
     assert np.abs(ener_vector(e) - ener_vector(ref)).max() < ETOL
+
+
+# ---------------------------------------------------------------------------------------------
+# k-points: one k-point of rhoofr_c and of vpsi's k-branch
+# ---------------------------------------------------------------------------------------------
+from helpers import golden_kpt_cases, load_golden_kpt  # noqa: E402
+
+
+@pytest.mark.parametrize("nr,ns,mb", [(16, 5, 2), (20, 4, 3), ((16, 20, 24), 3, 16), (30, 6, 1), (36, 2, 16)])
+def test_kpt_matches_oracle(emu_cdll, nr, ns, mb):
+    geo = orc.make_geometry(nr)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=mb, _cdll=emu_cdll)
+    c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns)
+    rho = np.full(geo.nnr1, 7.0)                                   # must be zeroed by the first k-point
+    ek, rg, rr = p.rhoofr_kpt_dev(c0, f, 0.4, hgkp, hgkm, rho)
+    ref = orc.rhoofr_kpt(geo, c0, f, 0.4, hgkp, hgkm, 1.3, 0.9)
+    assert relmax(rho, ref["rhoe"]) < RTOL
+    assert abs(ek - ref["ekin"]) < ETOL and abs(rg - ref["rsum_g"]) < ETOL and abs(rr - rg) < ETOL
+    # second k-point accumulates (rhoofr_c zeroes rhoe once, rhoofr_c_utils.mod.F90:107)
+    hg2p, hg2m = hgkm, hgkp                                        # k -> -k
+    ek2, rg2, rr2 = p.rhoofr_kpt_dev(c0[::-1].copy(), f, 0.6, hg2p, hg2m, rho, accumulate=True)
+    ref2 = orc.rhoofr_kpt(geo, c0[::-1], f, 0.6, hg2p, hg2m, 1.3, 0.9, rhoe=ref["rhoe"].copy())
+    assert relmax(rho, ref2["rhoe"]) < RTOL and abs(rr2 - (rg + rg2)) < ETOL
+    assert abs(ek2 - ref2["ekin"]) < ETOL
+    # vpsi k-branch: += and overwrite, ld > 2 ngw
+    ld = 2 * geo.ngw + 3
+    c0p = np.zeros((ns, ld), complex)
+    c0p[:, :2 * geo.ngw] = c0
+    c2 = np.full((ns, ld), 0.5 - 0.25j)
+    c2_ref = orc.vpsi_kpt(geo, c0, c2[:, :2 * geo.ngw].copy(), f, hgkp, hgkm, v, 0.9)
+    p.vpsi_kpt_dev(c0p, c2, f, hgkp, hgkm, v)
+    assert relmax(c2[:, :2 * geo.ngw], c2_ref) < RTOL
+    assert np.all(c2[:, 2 * geo.ngw:] == 0.5 - 0.25j)
+    p.vpsi_kpt_dev(c0p, c2, f, hgkp, hgkm, v, flags=lib.CPB_VPSI_OVERWRITE)
+    assert relmax(c2[:, :2 * geo.ngw], orc.vpsi_kpt(geo, c0, np.zeros_like(c0), f, hgkp, hgkm, v, 0.9)) < RTOL
+    # groups add up / partition the states
+    acc = np.zeros(geo.nnr1)
+    part = np.empty(geo.nnr1)
+    c2g = np.zeros_like(c0)
+    for g in range(2):
+        p.rhoofr_kpt_dev(c0, f, 0.4, hgkp, hgkm, part, ngroups=2, my_group=g)
+        acc += part
+        p.vpsi_kpt_dev(c0, c2g, f, hgkp, hgkm, v, ngroups=2, my_group=g)
+    assert relmax(acc, ref["rhoe"]) < RTOL
+    assert relmax(c2g, orc.vpsi_kpt(geo, c0, np.zeros_like(c0), f, hgkp, hgkm, v, 0.9)) < RTOL
+    # the Gamma entry points of the same plan are unaffected by the k-point calls
+    d = synthetic.make_inputs(geo.nr[0], 2) if isinstance(nr, int) else None
+    if d is not None:
+        pg = _plan(d, emu_cdll, max_batch=mb)
+        r0, *_ = pg.rhoofr(d["c0"], d["f"])
+        pg.rhoofr_kpt_dev(c0, f, 0.4, hgkp, hgkm, part)
+        r1, *_ = pg.rhoofr(d["c0"], d["f"])
+        assert np.array_equal(r0, r1)
+
+
+@pytest.mark.parametrize("path", golden_kpt_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_kpt_matches_golden(emu_cdll, path):
+    d = load_golden_kpt(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2, _cdll=emu_cdll)
+    rho = np.empty(p.nnr1)
+    ek, rg, rr = p.rhoofr_kpt_dev(d["c0"], d["f"], d["wk"], d["hgkp"], d["hgkm"], rho)
+    assert relmax(rho, d["rhoe"]) < RTOL and abs(ek - d["ekin"]) < ETOL and abs(rg - d["rsum_g"]) < ETOL
+    c2 = d["c2_in"].copy()
+    p.vpsi_kpt_dev(d["c0"], c2, d["f"], d["hgkp"], d["hgkm"], d["vpot"])
+    assert relmax(c2, d["c2_out"]) < RTOL
+
+
+def test_kpt_argument_checks(emu_cdll):
+    geo = orc.make_geometry(16)
+    p = Plan(geo.nr, geo.inyh, geo.hg, _cdll=emu_cdll)
+    c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, 2)
+    with pytest.raises(ValueError):
+        p.rhoofr_kpt_dev(c0[:, :geo.ngw].copy(), f, 1.0, hgkp, hgkm, np.empty(geo.nnr1))   # Gamma-sized c0
+    with pytest.raises(CpbError):
+        p.vpsi_kpt_dev(c0, np.zeros_like(c0), f, None, hgkm, v)

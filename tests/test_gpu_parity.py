@@ -377,3 +377,82 @@ def test_full_size_scf_step_properties(dev):
     dot = (w * (c0.real * c2.real + c0.imag * c2.imag)).sum().item()
     e_test = ekin + (v * rho).sum().item() / nn
     assert abs(-dot - e_test) < ETOL * max(1.0, abs(e_test))
+
+
+# ---------------------------------------------------------------------------------------------
+# k-points
+# ---------------------------------------------------------------------------------------------
+from helpers import golden_kpt_cases, load_golden_kpt  # noqa: E402
+
+
+@pytest.mark.parametrize("nr,ns,mb", [(16, 5, 2), ((16, 20, 24), 3, 16), (30, 6, 1), (48, 4, 3), (64, 5, 2),
+                                      (72, 3, 16), (96, 4, 2), (120, 3, 2)])
+def test_kpt_device_matches_oracle(dev, nr, ns, mb):
+    geo = orc.make_geometry(nr)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=mb)
+    c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    c0d, hp, hm, vd = t(c0), t(hgkp), t(hgkm), t(v)
+    rho = torch.full((geo.nnr1,), 7.0, dtype=torch.float64, device=dev)
+    ek, rg, rr = p.rhoofr_kpt_dev(c0d, f, 0.4, hp, hm, rho)
+    ref = orc.rhoofr_kpt(geo, c0, f, 0.4, hgkp, hgkm, 1.3, 0.9)
+    assert relmax(rho.cpu().numpy(), ref["rhoe"]) < RTOL
+    assert abs(ek - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"])) and abs(rg - ref["rsum_g"]) < ETOL
+    assert abs(rr - rg) < ETOL
+    ek2, rg2, rr2 = p.rhoofr_kpt_dev(t(c0[::-1]), f, 0.6, hm, hp, rho, accumulate=True)
+    ref2 = orc.rhoofr_kpt(geo, c0[::-1], f, 0.6, hgkm, hgkp, 1.3, 0.9, rhoe=ref["rhoe"].copy())
+    assert relmax(rho.cpu().numpy(), ref2["rhoe"]) < RTOL and abs(rr2 - (rg + rg2)) < ETOL
+    c2 = 0.3 * c0d
+    c2_ref = orc.vpsi_kpt(geo, c0, 0.3 * c0, f, hgkp, hgkm, v, 0.9)
+    p.vpsi_kpt_dev(c0d, c2, f, hp, hm, vd)
+    assert relmax(c2.cpu().numpy(), c2_ref) < RTOL
+    p.vpsi_kpt_dev(c0d, c2, f, hp, hm, vd, flags=lib.CPB_VPSI_OVERWRITE)
+    assert relmax(c2.cpu().numpy(), orc.vpsi_kpt(geo, c0, np.zeros_like(c0), f, hgkp, hgkm, v, 0.9)) < RTOL
+
+
+@pytest.mark.parametrize("path", golden_kpt_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_kpt_golden_vectors(dev, path):
+    d = load_golden_kpt(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    rho = torch.empty(p.nnr1, dtype=torch.float64, device=dev)
+    ek, rg, rr = p.rhoofr_kpt_dev(t(d["c0"]), d["f"], d["wk"], t(d["hgkp"]), t(d["hgkm"]), rho)
+    assert relmax(rho.cpu().numpy(), d["rhoe"]) < RTOL and abs(ek - d["ekin"]) < ETOL and abs(rg - d["rsum_g"]) < ETOL
+    c2 = t(d["c2_in"])
+    p.vpsi_kpt_dev(t(d["c0"]), c2, d["f"], t(d["hgkp"]), t(d["hgkm"]), t(d["vpot"]))
+    assert relmax(c2.cpu().numpy(), d["c2_out"]) < RTOL
+
+
+def test_kpt_full_size_properties(dev):
+    """192^3, 16 complex states at one k-point: charge identity, the k-point energy identity
+    -Re sum conj(c0) c2 = ekin + (1/N) sum V rho (all f != 0, wk = 1), k = 0 reduces to Gamma."""
+    n, ns = 192, 16
+    geo = orc.make_geometry(n)
+    p = Plan(geo.nr, geo.inyh, geo.hg, max_batch=8)
+    c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns)
+    f[:] = 2.0
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    c0d, hp, hm, vd = t(c0), t(hgkp), t(hgkm), t(v)
+    rho = torch.empty(geo.nnr1, dtype=torch.float64, device=dev)
+    ek, rg, rr = p.rhoofr_kpt_dev(c0d, f, 1.0, hp, hm, rho)
+    assert abs(rg - rr) < 1e-10 * rg and abs(rg - 2.0 * ns) < 1e-9
+    c2 = torch.zeros_like(c0d)
+    p.vpsi_kpt_dev(c0d, c2, f, hp, hm, vd)
+    lhs = -(c0d.conj() * c2).real.sum().item()
+    rhs = ek + (vd * rho).sum().item() / float(n) ** 3
+    assert abs(lhs - rhs) < ETOL * max(1.0, abs(rhs))
+    # k = 0 with [c, conj(c)] == the Gamma single-state path
+    d = synthetic.make_inputs(n, 3)
+    cg = torch.from_numpy(d["c0"]).to(dev)
+    ck = torch.cat([cg, cg.conj()], dim=1).contiguous()
+    ck[:, geo.ngw] = 0
+    hg = t(geo.hg)
+    rk = torch.empty_like(rho)
+    p.rhoofr_kpt_dev(ck, d["f"], 1.0, hg, hg, rk)
+    p.rhoofr_dev(cg, d["f"], rho)
+    assert relmax(rk.cpu().numpy(), rho.cpu().numpy()) < RTOL
+    c2k = torch.zeros_like(ck)
+    c2g = torch.zeros_like(cg)
+    p.vpsi_kpt_dev(ck, c2k, d["f"], hg, hg, vd)
+    p.vpsi_dev(cg, c2g, d["f"], vd)
+    assert relmax(c2k[:, :geo.ngw].cpu().numpy(), c2g.cpu().numpy()) < RTOL

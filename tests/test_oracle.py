@@ -317,3 +317,63 @@ def test_vofrho_golden_vectors_frozen():
         r = orc.vofrho_local(geo, d["rhoe"], d["scg"], d["eivps"], d["eirop"])
         assert np.abs(r["v"] - d["v"]).max() <= 1e-13 * np.abs(d["v"]).max()
         assert np.abs(r["rhog"] - d["rhog"]).max() <= 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# k-points: known answers
+# ---------------------------------------------------------------------------------------------
+
+def test_kpt_reduces_to_gamma_at_k0():
+    """A Gamma state c written as the k-point state [c, conj(c)] with k = 0 (hgkp = hgkm = hg) must
+    give the single-state Gamma results: same rho, ekin, charge, and C2 = [c2, conj(c2)]
+    (vpsi_utils.mod.F90:614-625 against :655-671 with one state per transform)."""
+    geo = orc.make_geometry(16)
+    cg, fg, vg = orc.synthetic_inputs(geo, 3, f_pattern="mixed")
+    fg = fg.copy()
+    ck = np.concatenate([cg, np.conj(cg)], axis=1)
+    ck[:, geo.ngw] = 0.0
+    rk = orc.rhoofr_kpt(geo, ck, fg, 1.0, geo.hg, geo.hg, 1.7, 0.8)
+    rg = orc.rhoofr(geo, cg, fg, 1.7, 0.8)
+    assert np.abs(rk["rhoe"] - rg["rhoe"]).max() < 1e-13 * np.abs(rg["rhoe"]).max()
+    assert abs(rk["ekin"] - rg["ekin"]) < 1e-12 and abs(rk["rsum_g"] - rg["rsum_g"]) < 1e-12
+    # f = 0: Gamma substitutes fi = 1 for f/2, the k-branch fi = 2 for f: the same force
+    occ = np.ones_like(fg, dtype=bool)
+    assert (fg == 0).any()
+    c2k = orc.vpsi_kpt(geo, ck, np.zeros_like(ck), fg, geo.hg, geo.hg, vg, 0.8)
+    c2g = orc.vpsi(geo, cg, np.zeros_like(cg), fg, vg, 0.8)
+    assert np.abs(c2k[occ, :geo.ngw] - c2g[occ]).max() < 1e-14
+    assert np.abs(c2k[occ, geo.ngw + 1:] - np.conj(c2g[occ, 1:])).max() < 1e-14
+    assert not c2k[:, geo.ngw].any()                                  # :625
+
+
+def test_kpt_known_answers():
+    """Single plane wave at -G: psi(r) = exp(-iG.r) (up to the centre-origin sign), so rho = wk f/omega
+    everywhere; constant potential: C2 = -f (tpiba2/2 |k+-G|^2 + v0) c0; charge identity."""
+    n = 16
+    geo = orc.make_geometry(n)
+    ngw = geo.ngw
+    c0 = np.zeros((1, 2 * ngw), complex)
+    c0[0, ngw + 7] = np.exp(0.3j)
+    _, _, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, 1)
+    f = np.array([2.0])
+    r = orc.rhoofr_kpt(geo, c0, f, 0.5, hgkp, hgkm, 1.5, 1.0)
+    box = r["rhoe"].reshape(geo.kr[2], geo.kr[1], geo.kr[0])[:n, :n, :n]
+    assert np.abs(box - 0.5 * 2.0 / 1.5).max() < 1e-14
+    assert abs(r["ekin"] - 0.5 * 0.5 * 2.0 * hgkm[7]) < 1e-14
+    c0r, f5, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, 5)
+    r = orc.rhoofr_kpt(geo, c0r, f5, 0.7, hgkp, hgkm, 1.5, 1.0)
+    assert abs(r["rhoe"].sum() * 1.5 / n ** 3 - r["rsum_g"]) < 1e-12
+    v0 = np.zeros_like(v)
+    v0.reshape(geo.kr[2], geo.kr[1], geo.kr[0])[:n, :n, :n] = -0.37
+    c2 = orc.vpsi_kpt(geo, c0r, np.zeros_like(c0r), f5, hgkp, hgkm, v0, 0.9)
+    fi = np.where(f5 == 0, 2.0, f5)[:, None]
+    want = -fi * (0.5 * 0.9 * np.concatenate([hgkp, hgkm]) - 0.37) * c0r
+    want[:, ngw] = 0.0
+    assert np.abs(c2 - want).max() < 1e-14
+    # energy identity per k-point: -Re sum conj(c0) c2 = 2 ekin/wk-part + int V rho (occupied states, fi = f)
+    occ = f5 != 0
+    c2 = orc.vpsi_kpt(geo, c0r, np.zeros_like(c0r), f5, hgkp, hgkm, v, 1.0)
+    r1 = orc.rhoofr_kpt(geo, c0r, f5, 1.0, hgkp, hgkm, 1.0, 1.0)
+    lhs = -np.sum((np.conj(c0r[occ]) * c2[occ]).real)
+    rhs = r1["ekin"] + np.dot(v, r1["rhoe"]) / n ** 3
+    assert abs(lhs - rhs) < 1e-12

@@ -32,6 +32,12 @@ VOFRHO_CASES = [
     ("n16x20x24", (16, 20, 24), 2.0, 1.1),
 ]
 
+KPT_CASES = [
+    # name, mesh, nstate, kvec, wk, omega, tpiba2
+    ("n16_s5", (16, 16, 16), 5, (0.25, 0.1, -0.3), 0.4, 1.3, 0.9),
+    ("n16x20x24_s3", (16, 20, 24), 3, (0.5, 0.0, 0.125), 1.0, 2.0, 1.1),
+]
+
 LSD_CASES = [
     # name, mesh, nstate, nsup, omega, tpiba2
     ("n16_s7_nsup3", (16, 16, 16), 7, 3, 1.3, 0.9),
@@ -82,6 +88,18 @@ def main():
                             nzh=dgeo.nzhs, indz=dgeo.indzs, omega=omega, tpiba2=tpiba2, rhoe=rhoe, scg=scg,
                             eivps=eivps, eirop=eirop, rhog=r["rhog"], vtemp=r["vtemp"], v=r["v"], ener=ener)
         print("vofrho/" + name, "nhg", dgeo.ngw)
+    # k-points (tests/golden/kpt/): one k-point of rhoofr_c and of vpsi's k-branch
+    os.makedirs(os.path.join(out, "kpt"), exist_ok=True)
+    for name, nr, ns, kvec, wk, omega, tpiba2 in KPT_CASES:
+        geo = orc.make_geometry(nr)
+        c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns, kvec=kvec, seed=555 + ns + nr[1])
+        rho = orc.rhoofr_kpt(geo, c0, f, wk, hgkp, hgkm, omega, tpiba2)
+        c2_in = 0.25 * c0[::-1].copy()
+        c2 = orc.vpsi_kpt(geo, c0, c2_in, f, hgkp, hgkm, v, tpiba2)
+        np.savez_compressed(os.path.join(out, "kpt", name + ".npz"), nr=np.array(nr), inyh=geo.inyh, hg=geo.hg,
+                            c0=c0, f=f, hgkp=hgkp, hgkm=hgkm, wk=wk, vpot=v, omega=omega, tpiba2=tpiba2,
+                            rhoe=rho["rhoe"], ekin=rho["ekin"], rsum_g=rho["rsum_g"], c2_in=c2_in, c2_out=c2)
+        print("kpt/" + name, "ngw", geo.ngw)
 
 
 if __name__ == "__main__":
