@@ -166,6 +166,9 @@ def _config(args, n_gpus):
                         f"({(args.states + 1) // 2} double-packed FFTs), {args.mesh}^3 mesh, dual 4",
             "mesh": args.mesh, "states": args.states, "pairs_per_batch": args.batch,
             "parallelism": f"cp_groups{n_gpus} (states sharded, rho allreduce, V broadcast)",
+            "collectives": (os.environ.get("CPB_COLLECTIVES", "peer") + (" (cpb_peer_* kernels over NVLink peer memory)"
+                            if os.environ.get("CPB_COLLECTIVES", "peer") == "peer" else " (torch.distributed)"))
+            if n_gpus > 1 else "none",
             "l2": "inputs larger than L2 (c0 block + intermediates >> 126 MB per step)"}
 
 
@@ -215,16 +218,35 @@ def run_ours(args, rank, world, local):
 
     c0 = c0_block_host.to(dev)
     c2 = torch.zeros_like(c0)
-    v = v_host.to(dev) if rank == 0 else torch.zeros(plan.nnr1, dtype=torch.float64, device=dev)
-    rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    # N > 1: rho and V live in an NVLink-mapped segment and the two collectives of the step are the
+    # library's own peer-memory kernels (cpb_peer_*); CPB_COLLECTIVES=nccl selects torch.distributed
+    collectives = os.environ.get("CPB_COLLECTIVES", "peer") if world > 1 else "none"
+    seg = None
+    nn = plan.nnr1 + (plan.nnr1 & 1)
+    if collectives == "peer":
+        seg = cdist.PeerSegment(2 * nn, rank, world, device=local)
+        rho = seg.tensor(0, plan.nnr1)
+        v = seg.tensor(nn, plan.nnr1)
+        v.zero_()
+        if rank == 0:
+            v.copy_(v_host, non_blocking=False)
+    else:
+        v = v_host.to(dev) if rank == 0 else torch.zeros(plan.nnr1, dtype=torch.float64, device=dev)
+        rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
+
+    def redist_and_bcast():
+        if seg is not None:
+            seg.allreduce(0, nn, stream=stream)        # cp_grp_redist(rhoe), rhoofr_utils.mod.F90:457-461
+            seg.bcast(nn, nn, src=0, stream=stream)    # V(r) once per step
+        elif world > 1:
+            cdist.cp_grp_redist(rho)
+            cdist.bcast_potential(v, src=0)
 
     def step_device():
         # rhoofr on the rank's block (local indices: the block is a contiguous state range)
         ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
-        if world > 1:
-            cdist.cp_grp_redist(rho)                   # rhoofr_utils.mod.F90:457-461
-            cdist.bcast_potential(v, src=0)            # V(r) once per step
+        redist_and_bcast()
         plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
         return ek, rg, rr
 
@@ -267,9 +289,7 @@ def run_ours(args, rank, world, local):
     # recomputed.  Reported separately as ms per CP step; `value` above never uses it.
     def step_device_keep():
         plan.rhoofr_dev(c0, f_block, rho, stream=stream, flags=lib.CPB_PSI_KEEP)
-        if world > 1:
-            cdist.cp_grp_redist(rho)
-            cdist.bcast_potential(v, src=0)
+        redist_and_bcast()
         plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_PSI_REUSE)
 
     ms_step_keep = timed(step_device_keep, max(1, min(args.steps, 3)), 1)
@@ -292,7 +312,10 @@ def run_ours(args, rank, world, local):
         plan.rhoofr(c0_block_host, f_block, rho_host, flags=lib.CPB_C0_KEEP)
         if world > 1:
             rho.copy_(rho_host, non_blocking=True)
-            cdist.cp_grp_redist(rho)
+            if seg is not None:
+                seg.allreduce(0, nn, stream=stream)
+            else:
+                cdist.cp_grp_redist(rho)
             rho_host.copy_(rho, non_blocking=True)
             torch.cuda.synchronize()
         plan.vpsi(c0_block_host, c2_block_host, f_block, v_host, flags=lib.CPB_C0_REUSE)
@@ -307,7 +330,10 @@ def run_ours(args, rank, world, local):
         plan.rhoofr(c0_block_host, f_block, rho_host, flags=lib.CPB_C0_KEEP)
         if world > 1:
             rho.copy_(rho_host, non_blocking=True)
-            cdist.cp_grp_redist(rho)
+            if seg is not None:
+                seg.allreduce(0, nn, stream=stream)
+            else:
+                cdist.cp_grp_redist(rho)
             rho_host.copy_(rho, non_blocking=True)
             torch.cuda.synchronize()
         plan.vpsi(c0_block_host, c2_block_host, f_block, v_host, flags=lib.CPB_C0_REUSE | lib.CPB_VPSI_OVERWRITE)

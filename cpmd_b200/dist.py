@@ -104,3 +104,102 @@ def bcast_potential(v, src=0, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(v, src=src, group=group)
     return v
+
+
+# ---------------------------------------------------------------------------------------------
+# cp_grp_redist / V broadcast as hand-written kernels over NVLink peer memory (cpb_peer_*)
+# ---------------------------------------------------------------------------------------------
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory (float64, 1-D) for torch.as_tensor."""
+
+    def __init__(self, ptr, n, owner):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class PeerSegment:
+    """One rank's segment of NVLink-mapped device memory plus the collectives that run on it
+    (``include/cpb200.h``: cpb_peer_*).  Arrays that take part in a collective are carved out of the
+    segment with :meth:`tensor`; offsets and sizes are in doubles.
+
+    ``exchange`` all-gathers the 64-byte handles: by default ``torch.distributed.all_gather_object``
+    over ``group``; tests pass their own (threads of one process on the kernel simulator)."""
+
+    def __init__(self, ndoubles, rank, world, device=0, exchange=None, group=None, _cdll=None):
+        import ctypes as C
+
+        from . import lib as _lib
+
+        self._L = _cdll if _cdll is not None else _lib.load()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        self.n = int(ndoubles) + (int(ndoubles) & 1)
+        self._h = C.c_void_p()
+        handle = (C.c_ubyte * _lib.CPB_PEER_HANDLE_BYTES)()
+        self._check(self._L.cpb_peer_create(C.byref(self._h), self.device, self.rank, self.world, self.n * 8, handle))
+        mine = bytes(handle)
+        if exchange is None:
+            import torch.distributed as dist
+
+            def exchange(b):
+                out = [None] * self.world
+                dist.all_gather_object(out, b, group=group)
+                return out
+        blobs = exchange(mine) if self.world > 1 else [mine]
+        allh = b"".join(blobs)
+        assert len(allh) == self.world * _lib.CPB_PEER_HANDLE_BYTES
+        buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+        self._check(self._L.cpb_peer_connect(self._h, buf))
+        self.ptr = int(self._L.cpb_peer_local_ptr(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"cpb_peer error {rc}: {self._L.cpb_peer_last_error().decode()}")
+
+    def tensor(self, offset, n):
+        """float64 CUDA tensor over doubles [offset, offset+n) of the local segment."""
+        import torch
+
+        if offset < 0 or offset + n > self.n:
+            raise ValueError("range outside the segment")
+        return torch.as_tensor(_DevArray(self.ptr + 8 * offset, n, self), device=torch.device("cuda", self.device))
+
+    def numpy(self, offset, n):
+        """Host view (kernel simulator only: its "device" memory is host memory)."""
+        import ctypes as C
+
+        import numpy as np
+        return np.ctypeslib.as_array((C.c_double * n).from_address(self.ptr + 8 * offset))
+
+    @staticmethod
+    def _sp(stream):
+        import ctypes as C
+        if stream is None:
+            return None
+        return C.c_void_p(stream if isinstance(stream, int) else stream.cuda_stream)
+
+    def allreduce(self, offset, n, stream=None):
+        """In-place sum over the ranks = cp_grp_redist (rhoofr_utils.mod.F90:457-461).  Enqueues only."""
+        self._check(self._L.cpb_peer_allreduce_f64(self._h, int(offset), int(n), self._sp(stream)))
+
+    def bcast(self, offset, n, src=0, stream=None):
+        self._check(self._L.cpb_peer_bcast_f64(self._h, int(offset), int(n), int(src), self._sp(stream)))
+
+    def barrier(self, stream=None):
+        self._check(self._L.cpb_peer_barrier(self._h, self._sp(stream)))
+
+    def check(self, stream=None):
+        """Synchronise the stream and raise if a barrier of an earlier collective timed out."""
+        self._check(self._L.cpb_peer_check(self._h, self._sp(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.cpb_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -28,6 +28,7 @@ CPB_C0_REUSE = 0x20
 CPB_PSI_KEEP = 0x40
 CPB_PSI_REUSE = 0x80
 CPB_DENSE_ACCUMULATE = 1
+CPB_PEER_HANDLE_BYTES = 64
 
 
 class PlanInfo(C.Structure):
@@ -97,6 +98,15 @@ SYMBOLS = {
                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
     "cpb_vpsi_kpt_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "cpb_peer_last_error": (C.c_char_p, []),
+    "cpb_peer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p]),
+    "cpb_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cpb_peer_local_ptr": (C.c_void_p, [C.c_void_p]),
+    "cpb_peer_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cpb_peer_check": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cpb_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "cpb_peer_bcast_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
+    "cpb_peer_destroy": (C.c_int, [C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),

@@ -239,6 +239,34 @@ int cpb_vpsi_kpt_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, 
                      const double* hgkp_dev, const double* hgkm_dev, const double* vpot_dev, int ngroups,
                      int my_group, unsigned flags, void* stream);
 
+/* ---- cross-group collectives over NVLink peer memory ----------------------------------------
+ * One process per GPU (the reference's CP_GROUPS layout, one group per MPI rank).  Each rank
+ * creates a SEGMENT of device memory, the ranks exchange the 64-byte handles with whatever they
+ * have (MPI_Allgather over cp_inter_grp in the Fortran host; torch.distributed in the Python
+ * harness) and map each other's segments (CUDA IPC).  Arrays that take part in a collective live
+ * inside the segment (rhoe, vpot: pass cpb_peer_local_ptr() + offset to cpb_rhoofr_dev / cpb_vpsi_dev).
+ *   cpb_peer_allreduce_f64  in-place sum over all ranks = cp_grp_redist(rhoe,nnr1,nlsd), i.e. mp_sum
+ *                           over parai%cp_inter_grp (rhoofr_utils.mod.F90:457-461,
+ *                           cp_grp_utils.mod.F90:98-120).  Deterministic (fixed rank order): all
+ *                           ranks end with bit-identical data.
+ *   cpb_peer_bcast_f64      rank `src`'s array to every rank (V(r) once per step).
+ * offset / n are in doubles and even.  Calls are collective: every rank must make the same sequence
+ * of calls.  cpb_peer_allreduce_f64 / cpb_peer_bcast_f64 only ENQUEUE their kernels on `stream` (later
+ * work on the same stream sees the result); cpb_peer_barrier and cpb_peer_check synchronise the stream
+ * and return CPB_ERR_CUDA if a rank failed to show up at a barrier within ~2 s (the kernels give up
+ * instead of hanging the device). */
+#define CPB_PEER_HANDLE_BYTES 64
+typedef struct cpb_peer cpb_peer;
+const char* cpb_peer_last_error(void);
+int cpb_peer_create(cpb_peer** seg, int device, int rank, int world, size_t bytes, void* handle_out);
+int cpb_peer_connect(cpb_peer* seg, const void* all_handles /* world * CPB_PEER_HANDLE_BYTES */);
+void* cpb_peer_local_ptr(cpb_peer* seg);
+int cpb_peer_barrier(cpb_peer* seg, void* stream);
+int cpb_peer_check(cpb_peer* seg, void* stream);
+int cpb_peer_allreduce_f64(cpb_peer* seg, size_t offset, size_t n, void* stream);
+int cpb_peer_bcast_f64(cpb_peer* seg, size_t offset, size_t n, int src, void* stream);
+int cpb_peer_destroy(cpb_peer* seg);
+
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);
 

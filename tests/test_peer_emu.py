@@ -1,0 +1,101 @@
+"""cpb_peer_* (collectives over peer memory) on the kernel simulator: the ranks are threads of one
+process whose "device" segments are host memory, so the slice arithmetic, the two-shot all-reduce,
+the two-phase broadcast and the flag barriers are exercised with real concurrency on the CPU.  The
+NVLink/IPC path itself is covered by tests/test_gpu_multi.py on a multi-GPU box."""
+import threading
+
+import numpy as np
+import pytest
+
+from cpmd_b200.dist import PeerSegment
+
+
+class _Exchange:
+    """all-gather of the handles between threads"""
+
+    def __init__(self, world):
+        self.world = world
+        self.slots = [None] * world
+        self.bar = threading.Barrier(world)
+
+    def make(self, rank):
+        def ex(b):
+            self.slots[rank] = b
+            self.bar.wait()
+            return list(self.slots)
+        return ex
+
+
+def _run(world, fn):
+    ex = _Exchange(world)
+    err = []
+
+    def body(r):
+        try:
+            fn(r, ex.make(r))
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+            try:
+                ex.bar.abort()
+            except Exception:
+                pass
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not err, err
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 4098), (4, 17 * 17 * 17 + 1), (8, 50)])
+def test_allreduce_and_bcast_threads_as_ranks(emu_cdll, world, n):
+    n += n & 1
+    rng = np.random.default_rng(world)
+    data = rng.standard_normal((world, n))
+    want = data[0].copy()
+    for q in range(1, world):
+        want = want + data[q]                     # the kernel's fixed rank order
+    vsrc = rng.standard_normal(n)
+    results = [None] * world
+    done = threading.Barrier(world)
+
+    def rank_fn(r, exchange):
+        seg = PeerSegment(2 * n + 6, r, world, exchange=exchange, _cdll=emu_cdll)
+        a = seg.numpy(0, n)
+        v = seg.numpy(n + 4, n)
+        a[:] = data[r]
+        v[:] = vsrc if r == 1 % world else -7.0
+        for _ in range(3):                        # repeated collectives: the epoch keeps increasing
+            a[:] = data[r]
+            seg.allreduce(0, n)
+            assert np.array_equal(a, want)
+        seg.bcast(n + 4, n, src=1 % world)
+        seg.check()
+        assert np.array_equal(v, vsrc)
+        guard = seg.numpy(n, 4)                   # words between the two arrays stay untouched
+        results[r] = a.copy()
+        seg.barrier()
+        done.wait()                               # nobody frees memory a peer may still read
+        del a, v, guard
+        seg.close()
+
+    _run(world, rank_fn)
+    for r in range(world):
+        assert np.array_equal(results[r], want)
+
+
+def test_argument_checks(emu_cdll):
+    seg = PeerSegment(64, 0, 1, _cdll=emu_cdll)
+    with pytest.raises(RuntimeError):
+        seg.allreduce(1, 10)                      # odd offset
+    with pytest.raises(RuntimeError):
+        seg.allreduce(0, 128)                     # outside the segment
+    with pytest.raises(RuntimeError):
+        seg.bcast(0, 64, src=3)
+    a = seg.numpy(0, 64)
+    a[:] = 2.5
+    seg.allreduce(0, 64)                          # world 1: identity
+    seg.bcast(0, 64, src=0)
+    assert np.all(a == 2.5)
+    seg.close()
