@@ -107,7 +107,7 @@ struct cpb_plan {
   const void* psi_key_ptr = nullptr;
   long psi_key[5] = {0, 0, 0, 0, 0};  // ld, nstate, ngroups, my_group, nsup
   double prologue_pairs = 0.25;  // block prologue cost in pair-times (pairs_per_group model)
-  int x_sub = 16;         // pairs per forward x-pass sub-batch (its band-ray storage G stays in L2)
+  int x_sub = 32;         // pairs per forward x-pass sub-batch (measured: fewer launches beat L2 residency of G, profiles/r01g_notes.txt)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable

@@ -80,9 +80,12 @@ struct KRange {
 };
 
 // resident blocks per SM the y/z kernels are compiled for (register budget 65536 / threads / this)
+#ifndef CPB_YZ_BLOCKS_SCALE
+#define CPB_YZ_BLOCKS_SCALE 1  // tuning builds with narrower blocks (CPB_B=4) ask for more of them
+#endif
 template <int R1, int R2>
 struct YZBlocks {
-  static constexpr int v = (MaxOf<R1, R2>::v <= 16 && R1 + R2 <= 28) ? 3 : 2;
+  static constexpr int v = ((MaxOf<R1, R2>::v <= 16 && R1 + R2 <= 28) ? 3 : 2) * CPB_YZ_BLOCKS_SCALE;
 };
 
 // Thread role a (0 <= a < RB) holds v[k] = x[a + RB*k] (zero outside k in [LO,HI)).  Radix-RA
