@@ -301,6 +301,27 @@ class Plan:
                                              _ptr(hgkm), _ptr(vpot), ngroups, my_group, flags, _stream_ptr(stream)))
         return c2
 
+    # -- meta-GGA (cntl%ttau): gk is the Fortran gk(3, ngw) = a C-order (ngw, 3) array ---------------
+    def tauofr_dev(self, c0, f, gk, tau, nsup=-1, nstate=None, ngroups=1, my_group=0, stream=None):
+        """``cpb_tauofr_dev``: tau (nnr1,) or (2, nnr1) with LSD, zeroed and written
+        (tauofr_utils.mod.F90:42-111)."""
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        need = (2 if nsup >= 0 else 1) * self.nnr1
+        if (tau.numel() if _is_torch(tau) else tau.size) < need:
+            raise ValueError("tau too small")
+        self._check(self._L.cpb_tauofr_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, int(nsup), _ptr(gk), ngroups,
+                                           my_group, _ptr(tau), 0, _stream_ptr(stream)))
+        return tau
+
+    def vtaupsi_dev(self, c0, c2, f, gk, vtau, nsup=-1, nstate=None, ngroups=1, my_group=0, stream=None):
+        """``cpb_vtaupsi_dev``: c2 -= ... (vtaupsi_utils.mod.F90:38-165); vtau (nnr1,) or (2, nnr1)."""
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        self._check(self._L.cpb_vtaupsi_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, int(nsup), _ptr(gk),
+                                            _ptr(vtau), ngroups, my_group, 0, _stream_ptr(stream)))
+        return c2
+
     # -- dense transforms on the density cutoff + local part of vofrho (plan built from nhg) --------
     # Arrays follow the package convention: Fortran (ld, nfields) = C-order (nfields, ld).
     def _dense_shapes(self, f, g):

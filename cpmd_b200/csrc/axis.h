@@ -21,6 +21,9 @@ struct AxisKernels {
   // grid.y), `half` = band-pruned instantiation
   void (*x_inv)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
                 int ppg, bool half);
+  // same with every coefficient scaled by +-gk[3*ig] (gradient component; tauofr / vtaupsi)
+  void (*x_inv_gk)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
+                   int ppg, bool half, const double* gk);
   void (*x_fwd)(cudaStream_t, const cplx* T1, cplx* G, const PlanDev&, int npair, int ppg, bool half);
   // y/z passes work on one chunk of x tiles [xt0, xt0+nxc) (T2 holds that chunk only); `half`
   // selects the band-pruned instantiation (KRange), `ppg` = pairs per block (pair groups in grid.z)

@@ -44,15 +44,31 @@ template <bool HALF>
 void x_inv_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
              int ppg) {
   using C = XCfg<R1, R2, SL>;
-  auto k = k_x_inv<R1, R2, SL, B, HALF>;
+  auto k = k_x_inv<R1, R2, SL, B, HALF, false>;
   const size_t smem = C::smem_inv(KRange<R1, HALF>::cnt);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg);
+  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg,
+             (const double*)nullptr);
 }
 void x_inv(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
            int ppg, bool half) {
   if (half) x_inv_t<true>(st, c0, ldc, T1, pd, pr, npair, ppg);
   else x_inv_t<false>(st, c0, ldc, T1, pd, pr, npair, ppg);
+}
+
+template <bool HALF>
+void x_inv_gk_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+                int ppg, const double* gk) {
+  using C = XCfg<R1, R2, SL>;
+  auto k = k_x_inv<R1, R2, SL, B, HALF, true>;
+  const size_t smem = C::smem_inv(KRange<R1, HALF>::cnt);
+  allow_smem(k, smem);
+  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg, gk);
+}
+void x_inv_gk(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+              int ppg, bool half, const double* gk) {
+  if (half) x_inv_gk_t<true>(st, c0, ldc, T1, pd, pr, npair, ppg, gk);
+  else x_inv_gk_t<false>(st, c0, ldc, T1, pd, pr, npair, ppg, gk);
 }
 
 template <bool HALF>
@@ -151,7 +167,7 @@ void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const
 }
 
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
-                            x_inv, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real, YZBlocks<R1, R2>::v,
+                            x_inv, x_inv_gk, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real, YZBlocks<R1, R2>::v,
                             XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD};
 
 }  // namespace

@@ -1445,4 +1445,153 @@ int cpb_vpsi_kpt_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------------------------
+// meta-GGA (cntl%ttau): tauofr and vtaupsi - the rhoofr / vpsi pipelines run once per Cartesian
+// direction on the gradient components d_k psi (dpsisc: coefficients scaled by +-gk(k,ig))
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+void run_x_inv_gk(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb,
+                  const double* gk_dir) {
+  Timed t(p, w.s, CPB_K_X_INV);
+  p->kx->x_inv_gk(w.s, c0, ldc, w.T1, p->pd, prb, nb, pairs_per_group(p, nb, p->nrp / p->kx->sl, p->kx->x_inv_blocks),
+                  p->half_x, gk_dir);
+}
+
+// tau0 / tau1: channel arrays (no LSD: n0 == np)
+void run_tauofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np, int n0, const double* gk, double* tau0,
+                double* tau1, cudaStream_t st) {
+  const std::vector<BatchSpan> batches = make_batches(p, np, n0);
+  const int nbatches = (int)batches.size();
+  fork_streams(p, st, nbatches);
+  for (int b = 0; b < nbatches; ++b) {
+    const int off = batches[b].off, nb = batches[b].n;
+    double* tau = batches[b].chan ? tau1 : tau0;
+    cpb_plan::WorkSpace& w = p->ws[b % p->nws];
+    PairDev prb = offset_pairs(pr, off);
+    for (int dir = 0; dir < 3; ++dir) {                                    // tauofr_utils.mod.F90:86-100
+      run_x_inv_gk(p, w, c0, ldc, prb, nb, gk + dir);
+      for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+        const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+        { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
+        if (b > 0 && p->nws > 1 && dir == 0) rt::stream_wait(w.s, p->ws[(b - 1) % p->nws].ev_rho);
+        { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, w.T2, tau, p->pd, prb, nb, xt0, nxc, p->half_z); }
+      }
+    }
+    rt::event_record(w.ev_rho, w.s);
+  }
+  join_streams(p, st, nbatches);
+  rt::check_last("tauofr kernels");
+}
+
+void run_vtaupsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr, int np, int n0, const double* gk,
+                 const double* v0, const double* v1, cudaStream_t st) {
+  const std::vector<BatchSpan> batches = make_batches(p, np, n0);
+  const int nbatches = (int)batches.size();
+  fork_streams(p, st, nbatches);
+  for (int b = 0; b < nbatches; ++b) {
+    const int off = batches[b].off, nb = batches[b].n;
+    const double* vtau = batches[b].chan ? v1 : v0;
+    cpb_plan::WorkSpace& w = p->ws[b % p->nws];
+    PairDev prb = offset_pairs(pr, off);
+    for (int dir = 0; dir < 3; ++dir) {                                    // vtaupsi_utils.mod.F90:68-88
+      run_x_inv_gk(p, w, c0, ldc, prb, nb, gk + dir);
+      for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
+        const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
+        const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm);
+        { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+        { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, w.T2, vtau, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
+        { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, w.T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      }
+      for (int o = 0; o < nb; o += p->x_sub) {
+        const int ns = std::min(p->x_sub, nb - o);
+        PairDev prs = offset_pairs(prb, o);
+        {
+          Timed t(p, w.s, CPB_K_X_FWD);
+          p->kx->x_fwd(w.s, w.T1 + (size_t)o * p->t1_pair, w.G, p->pd, ns,
+                       pairs_per_group(p, ns, p->nrp / p->kx->sl, p->kx->x_fwd_blocks), p->half_x);
+        }
+        Timed t(p, w.s, CPB_K_UNPACK);
+        const int ppg = ew_ppg(p, ns, 8);
+        auto k = k_unpack_tau;
+        CPB_LAUNCH(k, dim3((p->ngw + 255) / 256, (ns + ppg - 1) / ppg), dim3(256), 0, w.s, (const cplx*)w.G, c2, ldc,
+                   p->pd, prs, gk + dir, ns, ppg);
+      }
+    }
+  }
+  join_streams(p, st, nbatches);
+  rt::check_last("vtaupsi kernels");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb_tauofr_dev(cpb_plan* p, const void* c0_dev, long ld, int nstate, const double* f, int nsup,
+                   const double* gk_dev, int ngroups, int my_group, double* tau_dev, unsigned flags, void* stream) {
+  (void)flags;
+  if (int e = check_common(p, c0_dev, ld, nstate, f, ngroups, my_group)) return e;
+  if (!gk_dev || !tau_dev) return fail(CPB_ERR_INVALID, "null gk or tau");
+  if (nsup > nstate) return fail(CPB_ERR_INVALID, "nsup larger than nstate");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool lsd = nsup >= 0;
+    const size_t nnr1 = p->nnr1();
+    p->psi_valid = false;
+    std::vector<PairHost> pairs;
+    std::vector<double> cre, cim;
+    for (const PairHost& q : block_pairs(nstate, my_group, ngroups, nsup)) {
+      const double f1 = f[q.s1], f2 = q.s2 >= 0 ? f[q.s2] : 0.0;
+      if (f1 == 0.0 && f2 == 0.0) continue;  // adds nothing
+      pairs.push_back(q);
+      // tauadd (tauofr_utils.mod.F90:147-173): coef1 = tpiba2 f(is1) / (2 omega) weights AIMAG(psi)^2,
+      // coef2 (is2) weights REAL(psi)^2 - the gradient of a real state is imaginary
+      cim.push_back(0.5 * p->tpiba2 * f1 / p->omega);
+      cre.push_back(0.5 * p->tpiba2 * f2 / p->omega);
+    }
+    rt::dzero(tau_dev, (lsd ? 2 : 1) * nnr1 * sizeof(double), st);  // :80
+    run_tauofr(p, (const cplx*)c0_dev, ld, upload_pairs(p, pairs, cre, cim, st), (int)pairs.size(), count_chan0(pairs),
+               gk_dev, tau_dev, tau_dev + nnr1, st);
+    rt::sync(st);
+    resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+int cpb_vtaupsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f, int nsup,
+                    const double* gk_dev, const double* vtau_dev, int ngroups, int my_group, unsigned flags,
+                    void* stream) {
+  (void)flags;
+  if (int e = check_common(p, c0_dev, ld, nstate, f, ngroups, my_group)) return e;
+  if (!c2_dev || !gk_dev || !vtau_dev) return fail(CPB_ERR_INVALID, "null c2, gk or vtau");
+  if (nsup > nstate) return fail(CPB_ERR_INVALID, "nsup larger than nstate");
+  try {
+    rt::set_device(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    p->psi_valid = false;
+    const std::vector<PairHost> pairs = block_pairs(nstate, my_group, ngroups, nsup);
+    std::vector<double> fi1(pairs.size()), fi2(pairs.size());
+    for (size_t i = 0; i < pairs.size(); ++i) {
+      fi1[i] = 0.25 * f[pairs[i].s1] * p->tpiba2;                                   // vtaupsi_utils.mod.F90:143,154
+      fi2[i] = pairs[i].s2 >= 0 ? 0.25 * f[pairs[i].s2] * p->tpiba2 : 0.0;          // :155
+    }
+    run_vtaupsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi1, fi2, st), (int)pairs.size(),
+                count_chan0(pairs), gk_dev, vtau_dev, vtau_dev + p->nnr1(), st);
+    rt::sync(st);
+    resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+}  // extern "C"
+
 #include "host_api.inc"

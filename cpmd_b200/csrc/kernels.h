@@ -204,10 +204,12 @@ constexpr uint32_t kNegPW = 0x80000000u; // gtab: position holds the -G partner 
 // pair - no other thread touches those slots, so the gather needs no block barrier, holds no
 // registers while in flight and the coefficients come straight from c0 (no packed copy in
 // memory).  Positions without a plane wave are zeroed once.
-template <int R1, int R2, int SL, int B, bool HALF>
+// GK = true (tauofr / vtaupsi, dpsisc in tauofr_utils.mod.F90:113-137): every coefficient is multiplied by
+// gk[3*ig] (one Cartesian component of G, the caller passes gk + direction) at +G and by -gk[3*ig] at -G.
+template <int R1, int R2, int SL, int B, bool HALF, bool GK = false>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
     k_x_inv(const cplx* CPB_RESTRICT c0, long ldc, cplx* CPB_RESTRICT T1, PlanDev pd, PairDev pr, int npair,
-            int ppg) {
+            int ppg, const double* CPB_RESTRICT gk = nullptr) {
   using C = XCfg<R1, R2, SL>;
   using KR = KRange<R1, HALF>;
   constexpr int N = C::N, NT = C::NT, P1 = C::P1;
@@ -267,6 +269,10 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
           const double sg = (tab[j] & kNegPW) ? -1.0 : 1.0;
           // +G: c1 + i c2 = (a.x - b.y, a.y + b.x);  -G: conj(c1) + i conj(c2) = (a.x + b.y, b.x - a.y)
           v[k] = mk(a.x - sg * bq.y, sg * a.y + bq.x);
+          if constexpr (GK) {
+            const double g = (tab[j] != kNoPW) ? sg * __ldg(&gk[3 * (size_t)(tab[j] & ~kNegPW)]) : 0.0;
+            v[k] = cscale(v[k], g);
+          }
         } else {
           v[k] = mk(0.0, 0.0);
         }

@@ -294,4 +294,36 @@ CPB_GLOBAL k_unpack_kpt(const cplx* CPB_RESTRICT G, const cplx* CPB_RESTRICT c0,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// meta-GGA: ftauadd (vtaupsi_utils.mod.F90:131-165).  psi = FFT[vtau * d_k psi] at +-G from the band-ray
+// storage; c2(ig,is1) -= fi1 gk (Re fm, Im fp), c2(ig,is2) -= fi2 gk (Im fm, -Re fp), fp/fm = psi(+G) +- psi(-G),
+// gk = gk[3*ig] (caller passes gk + direction).  pr.ca/cb = fi1/fi2 = f tpiba2 / 4.
+// grid = (ceil(ngw/256), pair groups), block = 256
+// ---------------------------------------------------------------------------------------------
+CPB_GLOBAL k_unpack_tau(const cplx* CPB_RESTRICT G, cplx* CPB_RESTRICT c2, long ldc, PlanDev pd, PairDev pr,
+                        const double* CPB_RESTRICT gk, int npair, int ppg) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  const uint32_t lp = pd.gpos[ig], lm = pd.gneg[ig];
+  const double g = gk[3 * (size_t)ig];
+  const size_t g_pair = (size_t)pd.nxb * pd.nrp;
+  for (int pair = p0; pair < p1; ++pair) {
+    const int s1 = pr.st1[pair], s2 = pr.st2[pair];
+    const double f1 = pr.ca[pair] * g, f2 = pr.cb[pair] * g;
+    const cplx* gp = G + (size_t)pair * g_pair;
+    const cplx psin = gp[lp], psii = gp[lm];
+    const cplx fp = cadd(psin, psii), fm = csub(psin, psii);
+    cplx* o1 = c2 + (size_t)s1 * ldc + ig;
+    const cplx a = *o1;
+    *o1 = mk(a.x - f1 * fm.x, a.y - f1 * fp.y);
+    if (s2 >= 0) {
+      cplx* o2 = c2 + (size_t)s2 * ldc + ig;
+      const cplx b = *o2;
+      *o2 = mk(b.x - f2 * fm.y, b.y + f2 * fp.x);
+    }
+  }
+}
+
 }  // namespace cpb

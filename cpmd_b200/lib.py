@@ -107,6 +107,10 @@ SYMBOLS = {
     "cpb_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "cpb_peer_bcast_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
     "cpb_peer_destroy": (C.c_int, [C.c_void_p]),
+    "cpb_tauofr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
+    "cpb_vtaupsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),

@@ -267,6 +267,26 @@ int cpb_peer_allreduce_f64(cpb_peer* seg, size_t offset, size_t n, void* stream)
 int cpb_peer_bcast_f64(cpb_peer* seg, size_t offset, size_t n, int src, void* stream);
 int cpb_peer_destroy(cpb_peer* seg);
 
+/* ---- meta-GGA (cntl%ttau): kinetic-energy density and its potential ---------------------------
+ *   cpb_tauofr_dev   SUBROUTINE tauofr(c0,psi,nstate) (tauofr_utils.mod.F90:42-111): tau(r) = sum_i
+ *                    f_i tpiba2 / (2 omega) |grad psi_i(r)|^2 for the group's block, three sparse inverse
+ *                    transforms per state pair (dpsisc :113-137 scales the coefficients by +-gk(k,ig);
+ *                    tauadd :139-173).  tau_dev: (nnr1, nlsd), zeroed first (:80); with nsup >= 0 (LSD)
+ *                    column 1 = alpha, column 2 = beta (tauadd's ispin1/ispin2).  cp_grp_redist(tau) stays
+ *                    with the caller (:101-105; cpb_peer_allreduce_f64).
+ *   cpb_vtaupsi_dev  SUBROUTINE vtaupsi(c0,c2,f,psi,nstate,ispin) (vtaupsi_utils.mod.F90:38-92): c2 -=
+ *                    f tpiba2 / 4 * gk(k,ig) * unpack(FFT[vtau * d_k psi]) summed over k (taupot :94-129,
+ *                    ftauadd :131-165); always accumulates into c2.  vtau_dev: (nnr1, ispin).
+ * gk_dev: the cppt array gk(3,ngw) (column-major, Cartesian components of G in units of tpiba; gk(:,1) =
+ * 0 when G=0 is the first vector).  nsup < 0: no LSD.  The pair that straddles the spin boundary runs as
+ * two single states (same linear map as taupot's mixed branch). */
+int cpb_tauofr_dev(cpb_plan* plan, const void* c0_dev, long ld, int nstate, const double* f, int nsup,
+                   const double* gk_dev, int ngroups, int my_group, double* tau_dev, unsigned flags,
+                   void* stream);
+int cpb_vtaupsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                    int nsup, const double* gk_dev, const double* vtau_dev, int ngroups, int my_group,
+                    unsigned flags, void* stream);
+
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);
 

@@ -670,6 +670,91 @@ def synthetic_kpt_inputs(geo: Geometry, nstate, kvec=(0.25, 0.1, -0.3), seed=Non
     return c0, f, hgkp, hgkm, v.reshape(-1)
 
 
+# ----------------------------------------------------------------------------------------------
+# meta-GGA (cntl%ttau): tauofr / vtaupsi
+# ----------------------------------------------------------------------------------------------
+
+def gk_cartesian(geo: Geometry, b=None):
+    """cppt gk(3, ngw): Cartesian components of G in units of tpiba (rggen_utils.mod.F90:121-129,
+    gk(:,ig) = i b1 + j b2 + k b3); cubic cell by default.  Returned as (ngw, 3) C-order = Fortran (3, ngw)."""
+    nh = np.array([v // 2 + 1 for v in geo.nr])
+    ijk = (geo.inyh - nh[:, None]).astype(np.float64).T
+    if b is None:
+        return np.ascontiguousarray(ijk)
+    return np.ascontiguousarray(ijk @ np.asarray(b, dtype=np.float64))
+
+
+def dpsisc(geo: Geometry, gk, c1, c2, k):
+    """tauofr_utils.mod.F90:113-137: psi(nzhs) = gk(k,:) (c1 + i c2), psi(indzs) = -gk(k,:) (conj c1 + i conj c2),
+    psi(G=0) = 0; c2 = None for the single-state form."""
+    g = gk[:, k]
+    psi = np.zeros(geo.kr[0] * geo.nrays, dtype=np.complex128)
+    if c2 is None:
+        psi[geo.nzhs - 1] = g * c1
+        psi[geo.indzs - 1] = -g * np.conj(c1)
+    else:
+        psi[geo.nzhs - 1] = g * (c1 + 1j * c2)
+        psi[geo.indzs - 1] = -g * (np.conj(c1) + 1j * np.conj(c2))
+    if geo.geq0:
+        psi[geo.nzhs[0] - 1] = 0.0
+    return psi
+
+
+def tauofr(geo: Geometry, c0, f, gk, omega, tpiba2, nsup=None, group=0, ngroups=1):
+    """``tauofr`` (tauofr_utils.mod.F90:42-111) with tauadd (:139-173).  Returns tau (nlsd, nnr1): the
+    group's partial sum (cp_grp_redist :101-105 is the caller's)."""
+    nstate = c0.shape[0]
+    nlsd = 1 if nsup is None else 2
+    tau = np.zeros((nlsd, geo.nnr1))
+    for is1, is2 in state_pairs(nstate, group, ngroups):
+        coef1 = 0.5 * tpiba2 * f[is1] / omega                                  # :147
+        coef2 = 0.0 if is2 is None else 0.5 * tpiba2 * f[is2] / omega          # :148-152
+        for k in range(3):                                                     # :86-100
+            psi = invfftn_sparse(geo, dpsisc(geo, gk, c0[is1], None if is2 is None else c0[is2], k))
+            r1, r2 = psi.imag, psi.real                                        # :161-162
+            if nsup is None:
+                tau[0] += coef1 * r1 * r1 + coef2 * r2 * r2                    # :171
+            else:
+                sp1 = 1 if (is1 + 1) > nsup else 0                             # :156
+                sp2 = 1 if ((nstate + 1) if is2 is None else (is2 + 1)) > nsup else 0   # :157
+                tau[sp1] += coef1 * r1 * r1                                    # :163
+                tau[sp2] += coef2 * r2 * r2                                    # :164
+    return tau
+
+
+def vtaupsi(geo: Geometry, c0, c2, f, gk, vtau, tpiba2, nsup=None, group=0, ngroups=1):
+    """``vtaupsi`` (vtaupsi_utils.mod.F90:38-92) with taupot (:94-129) and ftauadd (:131-165).
+    vtau: (ispin, nnr1).  Returns the updated c2 (a copy)."""
+    nstate = c0.shape[0]
+    out = c2.copy()
+    vt = np.atleast_2d(vtau)
+    for is1, is2 in state_pairs(nstate, group, ngroups):
+        fi1 = 0.25 * f[is1] * tpiba2
+        fi2 = 0.0 if is2 is None else 0.25 * f[is2] * tpiba2
+        for k in range(3):
+            psi = invfftn_sparse(geo, dpsisc(geo, gk, c0[is1], None if is2 is None else c0[is2], k))
+            if nsup is None:
+                psi = psi * vt[0]                                              # :104-107
+            else:
+                i2 = (nstate + 1) if is2 is None else (is2 + 1)
+                if i2 <= nsup:
+                    psi = psi * vt[0]                                          # :109-113
+                elif (is1 + 1) > nsup:
+                    psi = psi * vt[1]                                          # :114-118
+                else:
+                    psi = psi.real * vt[1] + 1j * psi.imag * vt[0]             # :119-125
+            psi = fwfftn_sparse(geo, psi)
+            psin = psi[geo.nzhs - 1]
+            psii = psi[geo.indzs - 1]
+            fp = psin + psii
+            fm = psin - psii
+            g = gk[:, k]
+            out[is1] -= fi1 * g * (fm.real + 1j * fp.imag)                     # :147-148 / :160-161
+            if is2 is not None:
+                out[is2] -= fi2 * g * (fm.imag - 1j * fp.real)                 # :162-163
+    return out
+
+
 def e_test(geo: Geometry, rho_out, vpot, omega):
     """The synthetic "total energy" used for the 1e-9 Ha criterion:
     E_test = ekin + (Omega/N) * sum_r V(r) rho(r)."""

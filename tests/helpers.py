@@ -82,3 +82,17 @@ def load_golden_kpt(path):
         d[k] = float(d[k])
     d["nr"] = tuple(int(v) for v in d["nr"])
     return d
+
+
+def golden_tau_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, "tau", "*.npz")))
+
+
+def load_golden_tau(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    for k in ("omega", "tpiba2"):
+        d[k] = float(d[k])
+    d["nsup"] = int(d["nsup"])
+    d["nr"] = tuple(int(v) for v in d["nr"])
+    return d

@@ -482,3 +482,50 @@ def test_kpt_argument_checks(emu_cdll):
         p.rhoofr_kpt_dev(c0[:, :geo.ngw].copy(), f, 1.0, hgkp, hgkm, np.empty(geo.nnr1))   # Gamma-sized c0
     with pytest.raises(CpbError):
         p.vpsi_kpt_dev(c0, np.zeros_like(c0), f, None, hgkm, v)
+
+
+# ---------------------------------------------------------------------------------------------
+# meta-GGA tauofr / vtaupsi
+# ---------------------------------------------------------------------------------------------
+from helpers import golden_tau_cases, load_golden_tau  # noqa: E402
+
+
+@pytest.mark.parametrize("nr,ns,mb,nsup", [(16, 5, 2, None), (20, 4, 3, None), (16, 7, 2, 3), ((16, 20, 24), 6, 16, 4),
+                                           (30, 3, 1, 0), (36, 2, 16, None)])
+def test_tau_matches_oracle(emu_cdll, nr, ns, mb, nsup):
+    geo = orc.make_geometry(nr)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=mb, _cdll=emu_cdll)
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    gk = orc.gk_cartesian(geo)
+    nl = 1 if nsup is None else 2
+    cs = -1 if nsup is None else nsup
+    tau = np.full((nl, geo.nnr1), 7.0)
+    p.tauofr_dev(c0, f, gk, tau, nsup=cs)
+    ref = orc.tauofr(geo, c0, f, gk, 1.3, 0.9, nsup)
+    assert np.abs(tau - ref).max() / np.abs(ref).max() < RTOL
+    vt = np.ascontiguousarray(np.stack([v, 0.5 * v[::-1]])[:nl])
+    c2 = 0.3 * c0
+    c2_ref = orc.vtaupsi(geo, c0, c2, f, gk, vt, 0.9, nsup)
+    p.vtaupsi_dev(c0, c2, f, gk, vt, nsup=cs)
+    assert relmax(c2, c2_ref) < RTOL
+    # groups: partial tau adds up, c2 blocks partition
+    acc = np.zeros((nl, geo.nnr1))
+    part = np.empty((nl, geo.nnr1))
+    c2g = 0.3 * c0
+    for g in range(2):
+        p.tauofr_dev(c0, f, gk, part, nsup=cs, ngroups=2, my_group=g)
+        acc += part
+        p.vtaupsi_dev(c0, c2g, f, gk, vt, nsup=cs, ngroups=2, my_group=g)
+    assert np.abs(acc - ref).max() / np.abs(ref).max() < RTOL and relmax(c2g, c2_ref) < RTOL
+
+
+@pytest.mark.parametrize("path", golden_tau_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_tau_matches_golden(emu_cdll, path):
+    d = load_golden_tau(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2, _cdll=emu_cdll)
+    tau = np.empty_like(d["tau"])
+    p.tauofr_dev(d["c0"], d["f"], d["gk"], tau, nsup=d["nsup"])
+    assert np.abs(tau - d["tau"]).max() / np.abs(d["tau"]).max() < RTOL
+    c2 = d["c2_in"].copy()
+    p.vtaupsi_dev(d["c0"], c2, d["f"], d["gk"], np.ascontiguousarray(d["vtau"]), nsup=d["nsup"])
+    assert relmax(c2, d["c2_out"]) < RTOL

@@ -456,3 +456,67 @@ def test_kpt_full_size_properties(dev):
     p.vpsi_kpt_dev(ck, c2k, d["f"], hg, hg, vd)
     p.vpsi_dev(cg, c2g, d["f"], vd)
     assert relmax(c2k[:, :geo.ngw].cpu().numpy(), c2g.cpu().numpy()) < RTOL
+
+
+# ---------------------------------------------------------------------------------------------
+# meta-GGA tauofr / vtaupsi
+# ---------------------------------------------------------------------------------------------
+from helpers import golden_tau_cases, load_golden_tau  # noqa: E402
+
+
+@pytest.mark.parametrize("nr,ns,mb,nsup", [(16, 5, 2, None), ((16, 20, 24), 6, 16, 4), (30, 3, 1, 0), (48, 5, 2, 2),
+                                           (64, 4, 16, None), (96, 3, 2, None), (120, 2, 2, None)])
+def test_tau_device_matches_oracle(dev, nr, ns, mb, nsup):
+    geo = orc.make_geometry(nr)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=mb)
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    gk = orc.gk_cartesian(geo)
+    nl = 1 if nsup is None else 2
+    cs = -1 if nsup is None else nsup
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    c0d, gkd = t(c0), t(gk)
+    tau = torch.full((nl, geo.nnr1), 7.0, dtype=torch.float64, device=dev)
+    p.tauofr_dev(c0d, f, gkd, tau, nsup=cs)
+    ref = orc.tauofr(geo, c0, f, gk, 1.3, 0.9, nsup)
+    assert np.abs(tau.cpu().numpy() - ref).max() / np.abs(ref).max() < RTOL
+    vt = np.ascontiguousarray(np.stack([v, 0.5 * v[::-1]])[:nl])
+    c2 = 0.3 * c0d
+    c2_ref = orc.vtaupsi(geo, c0, 0.3 * c0, f, gk, vt, 0.9, nsup)
+    p.vtaupsi_dev(c0d, c2, f, gkd, t(vt), nsup=cs)
+    assert relmax(c2.cpu().numpy(), c2_ref) < RTOL
+
+
+@pytest.mark.parametrize("path", golden_tau_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_tau_golden_vectors(dev, path):
+    d = load_golden_tau(path)
+    p = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    tau = torch.empty(d["tau"].shape, dtype=torch.float64, device=dev)
+    p.tauofr_dev(t(d["c0"]), d["f"], t(d["gk"]), tau, nsup=d["nsup"])
+    assert np.abs(tau.cpu().numpy() - d["tau"]).max() / np.abs(d["tau"]).max() < RTOL
+    c2 = t(d["c2_in"])
+    p.vtaupsi_dev(t(d["c0"]), c2, d["f"], t(d["gk"]), t(d["vtau"]), nsup=d["nsup"])
+    assert relmax(c2.cpu().numpy(), d["c2_out"]) < RTOL
+
+
+def test_tau_full_size_properties(dev):
+    """192^3, 16 states: int tau = ekin of rhoofr, -sum dotp(c0, dC2) = int vtau tau, tau >= 0."""
+    n, ns = 192, 16
+    d = synthetic.make_inputs(n, ns)
+    geo = orc.make_geometry(n)
+    p = Plan(d["nr"], d["inyh"], d["hg"], max_batch=8)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    c0, gk, v = t(d["c0"]), t(orc.gk_cartesian(geo)), t(d["vpot"])
+    rho = torch.empty(p.nnr1, dtype=torch.float64, device=dev)
+    ekin, rg, rr = p.rhoofr_dev(c0, d["f"], rho)
+    tau = torch.empty(p.nnr1, dtype=torch.float64, device=dev)
+    p.tauofr_dev(c0, d["f"], gk, tau)
+    nn = float(n) ** 3
+    assert abs(tau.sum().item() / nn - ekin) < ETOL * max(1.0, ekin) and tau.min().item() >= 0.0
+    c2 = torch.zeros_like(c0)
+    p.vtaupsi_dev(c0, c2, d["f"], gk, v)
+    w = torch.full((p.ngw,), 2.0, dtype=torch.float64, device=dev)
+    w[0] = 1.0
+    lhs = -(w * (c0.real * c2.real + c0.imag * c2.imag)).sum().item()
+    rhs = (v * tau).sum().item() / nn
+    assert abs(lhs - rhs) < ETOL * max(1.0, abs(rhs))

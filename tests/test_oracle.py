@@ -377,3 +377,48 @@ def test_kpt_known_answers():
     lhs = -np.sum((np.conj(c0r[occ]) * c2[occ]).real)
     rhs = r1["ekin"] + np.dot(v, r1["rhoe"]) / n ** 3
     assert abs(lhs - rhs) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# meta-GGA tauofr / vtaupsi: known answers
+# ---------------------------------------------------------------------------------------------
+
+def test_tau_known_answers():
+    """int tau(r) dr = ekin (tauadd's tpiba2 f / (2 omega) |grad psi|^2 against kin_energy); a single
+    plane wave gives tau = (f tpiba2 / 2 omega) 4 |G|^2 sin^2(G.r + phi); constant vtau = v0 turns vtaupsi
+    into c2 -= f/2 v0 tpiba2 |G|^2 c0; and -sum dotp(c0, dC2) = (1/N) sum vtau(r) tau(r) omega."""
+    n = 16
+    geo = orc.make_geometry(n)
+    gk = orc.gk_cartesian(geo)
+    assert np.allclose((gk ** 2).sum(axis=1), geo.hg) and not gk[0].any()
+    c0, f, v = orc.synthetic_inputs(geo, 3, f_pattern="mixed")
+    f[1] = 2.0
+    omega, tp = 1.7, 0.8
+    tau = orc.tauofr(geo, c0, f, gk, omega, tp)[0]
+    r = orc.rhoofr(geo, c0, f, omega, tp)
+    assert abs(tau.sum() * omega / n ** 3 - r["ekin"]) < 1e-12
+    assert tau.min() >= 0.0
+    # single plane wave
+    ig, phi = 9, 0.4
+    c1 = np.zeros((1, geo.ngw), complex)
+    c1[0, ig] = np.exp(1j * phi)
+    t1 = orc.tauofr(geo, c1, np.array([2.0]), gk, omega, tp)[0].reshape(geo.kr[2], geo.kr[1], geo.kr[0])[:n, :n, :n]
+    z, y, x = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    arg = 2 * np.pi * (gk[ig, 0] * x + gk[ig, 1] * y + gk[ig, 2] * z) / n + phi
+    want = 2.0 * tp / (2 * omega) * 4 * geo.hg[ig] * np.sin(arg) ** 2
+    assert np.abs(t1 - want).max() < 1e-13
+    # constant potential
+    v0 = np.zeros_like(v)
+    v0.reshape(geo.kr[2], geo.kr[1], geo.kr[0])[:n, :n, :n] = -0.37
+    d = orc.vtaupsi(geo, c0, np.zeros_like(c0), f, gk, v0[None], tp)
+    assert np.abs(d + f[:, None] * 0.5 * (-0.37) * tp * geo.hg * c0).max() < 1e-15
+    # energy identity with a general potential
+    d = orc.vtaupsi(geo, c0, np.zeros_like(c0), f, gk, v[None], tp)
+    lhs = -sum(orc.dotp(geo, c0[i], d[i]) for i in range(3))
+    assert abs(lhs - np.dot(v, tau) * omega / n ** 3) < 1e-12
+    # LSD: the channels add up to the unpolarised tau, pair packing is irrelevant
+    for nsup in (0, 1, 2, 3):
+        t2 = orc.tauofr(geo, c0, f, gk, omega, tp, nsup)
+        assert np.abs(t2.sum(axis=0) - tau).max() < 1e-14
+        d2 = orc.vtaupsi(geo, c0, np.zeros_like(c0), f, gk, np.stack([v, v]), tp, nsup)
+        assert np.abs(d2 - d).max() < 1e-15

@@ -38,6 +38,12 @@ KPT_CASES = [
     ("n16x20x24_s3", (16, 20, 24), 3, (0.5, 0.0, 0.125), 1.0, 2.0, 1.1),
 ]
 
+TAU_CASES = [
+    # name, mesh, nstate, nsup (None: no LSD), omega, tpiba2
+    ("n16_s5", (16, 16, 16), 5, None, 1.7, 0.8),
+    ("n16x20x24_s4_nsup1", (16, 20, 24), 4, 1, 2.0, 1.1),
+]
+
 LSD_CASES = [
     # name, mesh, nstate, nsup, omega, tpiba2
     ("n16_s7_nsup3", (16, 16, 16), 7, 3, 1.3, 0.9),
@@ -100,6 +106,20 @@ def main():
                             c0=c0, f=f, hgkp=hgkp, hgkm=hgkm, wk=wk, vpot=v, omega=omega, tpiba2=tpiba2,
                             rhoe=rho["rhoe"], ekin=rho["ekin"], rsum_g=rho["rsum_g"], c2_in=c2_in, c2_out=c2)
         print("kpt/" + name, "ngw", geo.ngw)
+    # meta-GGA (tests/golden/tau/): tauofr + vtaupsi
+    os.makedirs(os.path.join(out, "tau"), exist_ok=True)
+    for name, nr, ns, nsup, omega, tpiba2 in TAU_CASES:
+        geo = orc.make_geometry(nr)
+        c0, f, v = orc.synthetic_inputs(geo, ns, seed=321 + ns + nr[2], f_pattern="mixed")
+        gk = orc.gk_cartesian(geo)
+        tau = orc.tauofr(geo, c0, f, gk, omega, tpiba2, nsup)
+        vtau = np.stack([v, 0.5 * v[::-1]])[: (1 if nsup is None else 2)]
+        c2_in = 0.25 * c0[::-1].copy()
+        c2 = orc.vtaupsi(geo, c0, c2_in, f, gk, vtau, tpiba2, nsup)
+        np.savez_compressed(os.path.join(out, "tau", name + ".npz"), nr=np.array(nr), inyh=geo.inyh, hg=geo.hg,
+                            c0=c0, f=f, gk=gk, nsup=-1 if nsup is None else nsup, omega=omega, tpiba2=tpiba2,
+                            tau=tau, vtau=vtau, c2_in=c2_in, c2_out=c2)
+        print("tau/" + name, "ngw", geo.ngw)
 
 
 if __name__ == "__main__":
