@@ -529,3 +529,28 @@ def test_tau_matches_golden(emu_cdll, path):
     c2 = d["c2_in"].copy()
     p.vtaupsi_dev(d["c0"], c2, d["f"], d["gk"], np.ascontiguousarray(d["vtau"]), nsup=d["nsup"])
     assert relmax(c2, d["c2_out"]) < RTOL
+
+
+def test_empty_and_degenerate_inputs(emu_cdll):
+    """Ragged / empty inputs the reference loops handle implicitly: no states, one state, a group with
+    no states (more groups than states), all occupations zero."""
+    geo = orc.make_geometry(16)
+    p = Plan(geo.nr, geo.inyh, geo.hg, _cdll=emu_cdll, max_batch=2)
+    c0, f, v = orc.synthetic_inputs(geo, 1)
+    rho, ek, rg, rr = p.rhoofr(c0, f)
+    ref = orc.rhoofr(geo, c0, f, 1.0, 1.0)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL and abs(rg - rr) < ETOL
+    c2 = np.zeros_like(c0)
+    p.vpsi(c0, c2, f, v)
+    assert relmax(c2, orc.vpsi(geo, c0, np.zeros_like(c0), f, v, 1.0)) < RTOL
+    c00 = np.zeros((0, geo.ngw), complex)
+    rho, ek, rg, rr = p.rhoofr(c00, np.zeros(0))
+    assert not rho.any() and (ek, rg, rr) == (0.0, 0.0, 0.0)
+    p.vpsi(c00, np.zeros_like(c00), np.zeros(0), v)
+    rho, ek, rg, rr = p.rhoofr(c0, f, ngroups=3, my_group=2)          # this group owns no state
+    assert not rho.any() and (ek, rg, rr) == (0.0, 0.0, 0.0)
+    rho, ek, rg, rr = p.rhoofr(c0, np.zeros(1))                        # nothing occupied: rho = 0
+    assert not rho.any() and (ek, rg, rr) == (0.0, 0.0, 0.0)
+    c2 = np.zeros_like(c0)
+    p.vpsi(c0, c2, np.zeros(1), v)                                     # vpsi still acts (fi = 1)
+    assert relmax(c2, orc.vpsi(geo, c0, np.zeros_like(c0), np.zeros(1), v, 1.0)) < RTOL
