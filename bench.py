@@ -192,6 +192,72 @@ def cpu_baseline(args):
             "sample": f"{ns} of {args.states} states, mesh {n}^3, rhoofr+vpsi once ({dt:.1f} s)"}
 
 
+def widened_rows(args, dev, plan, c0, f_block, v, timed):
+    """Measurements for the SURVEY 8(f) rows built next to the hot path (N=1 only; device-resident,
+    CUDA events, 3 warm-up + 5 timed calls each): the local part of vofrho on the density cutoff,
+    one k-point of rhoofr_c + vpsi's k-branch, tauofr + vtaupsi.  Reported beside, never inside, `value`."""
+    import torch
+
+    from cpmd_b200 import Plan, gvec
+
+    out = {}
+    n = args.mesh
+    nst = min(64, c0.shape[0])
+    # ---- vofrho_local: rho -> rho(G) -> ppener -> V(r) on a plan built from the nhg list
+    inyh_d, hg_d = gvec.half_sphere((n, n, n), (n / 2.0) ** 2)
+    dplan = Plan((n, n, n), inyh_d, hg_d, device=dev.index or 0, max_batch=1)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    nhg = dplan.ngw
+    scg = torch.zeros(nhg, dtype=torch.float64)
+    scg[1:] = 4.0 * np.pi / torch.from_numpy(hg_d[1:])
+    eivps = torch.complex(torch.randn(nhg, generator=g, dtype=torch.float64), torch.randn(nhg, generator=g, dtype=torch.float64))
+    eirop = 0.1 * torch.complex(torch.randn(nhg, generator=g, dtype=torch.float64), torch.randn(nhg, generator=g, dtype=torch.float64))
+    scg, eivps, eirop = scg.to(dev), eivps.to(dev), eirop.to(dev)
+    rho = torch.rand(dplan.nnr1, dtype=torch.float64, device=dev)
+    vloc = torch.empty_like(rho)
+    l0 = dplan.launch_count
+    ms = timed(lambda: dplan.vofrho_local_dev(rho, scg, eivps, eirop, vloc), 5, 3)
+    dense_bytes = 2 * (8.0 * n ** 3 + 2 * 16.0 * n * n * dplan.info["zband"] + 2 * 16.0 * n * dplan.info["nrays"] + 16.0 * nhg)
+    out["vofrho_local"] = {"ms_per_call": ms, "nhg": nhg, "launches_per_call": (dplan.launch_count - l0) // 8,
+                           "algorithmic_GB_per_s": dense_bytes / (ms * 1e-3) / 1e9,
+                           "note": "dense forward + ppener + dense inverse on the density-cutoff plan (DESIGN 3b)"}
+    del dplan, rho, vloc
+    # ---- k-points: complex states [c(+G), c(-G)], one k-point
+    ngw = plan.ngw
+    ck = torch.cat([c0[:nst], torch.flip(c0[:nst], dims=[0]).conj()], dim=1).contiguous()
+    ck[:, ngw] = 0
+    hg = torch.from_numpy(np.ascontiguousarray(gvec.half_sphere((n, n, n))[1])).to(dev)
+    hgkp, hgkm = hg + 0.3, hg + 0.1
+    fk = np.full(nst, 2.0)
+    rhok = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    c2k = torch.zeros_like(ck)
+
+    def step_k():
+        plan.rhoofr_kpt_dev(ck, fk, 1.0, hgkp, hgkm, rhok)
+        plan.vpsi_kpt_dev(ck, c2k, fk, hgkp, hgkm, v)
+
+    ms = timed(step_k, 5, 3)
+    out["kpoints"] = {"ms_per_step": ms, "states": nst, "band_ffts_per_s": 3.0 * nst / (ms * 1e-3),
+                      "note": "one k-point: rhoofr_c inner loop + vpsi k-branch, one complex state per transform (DESIGN 3c)"}
+    del ck, c2k, rhok
+    # ---- meta-GGA: tauofr (3 transforms per pair) + vtaupsi (6)
+    nh = n // 2 + 1
+    gk = torch.from_numpy(np.ascontiguousarray((gvec.half_sphere((n, n, n))[0].T - nh).astype(np.float64))).to(dev)
+    tau = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    c2t = torch.zeros_like(c0[:nst])
+    c0t = c0[:nst].contiguous()
+    ft = np.ascontiguousarray(f_block[:nst])
+
+    def step_tau():
+        plan.tauofr_dev(c0t, ft, gk, tau)
+        plan.vtaupsi_dev(c0t, c2t, ft, gk, v)
+
+    ms = timed(step_tau, 5, 3)
+    out["meta_gga"] = {"ms_per_step": ms, "states": nst, "band_ffts_per_s": 9.0 * nst / (ms * 1e-3),
+                       "note": "tauofr + vtaupsi: 3 + 6 band-FFTs per state (DESIGN 3d)"}
+    return out
+
+
 def run_ours(args, rank, world, local):
     import torch
     import torch.distributed as dist
@@ -347,6 +413,10 @@ def run_ours(args, rank, world, local):
         d2h += plan.nnr1 * 8
     e2e_value = 3.0 * nstate / (ms_e2e * 1e-3)
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = widened_rows(args, dev, plan, c0, f_block, v, timed)
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (largest share of the step)
@@ -398,6 +468,8 @@ def run_ours(args, rank, world, local):
                      "ms_per_step_serialised": ms_step_serial,
                      "kernel_ms_per_step": {k: v_[0] / prof_steps for k, v_ in ktimes.items()}},
     }
+    if extras is not None:
+        line["widened_rows"] = extras
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
@@ -418,6 +490,7 @@ def main():
     ap.add_argument("--cpu-sample-states", type=int, default=512,
                     help="states of the cpu_baseline leg (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the widened-row measurements (vofrho, k-points, tau)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -33,9 +33,10 @@
  * Layout conventions are the reference's: c0/c2 are column-major (ld, nstate) COMPLEX*16, one
  * column per state, ngw <= ld; rhoe/vpot are REAL*8 (kr1, kr2s, kr3s) x-fastest with the
  * odd-padded leading dimensions of leadim (loadpa_utils.mod.F90:509-525); inyh is INTEGER*4
- * (3,ngw), 1-based.  Implemented variants: Gamma point, RKS and LSD; no LSE, no
- * tau, no double grid, akin = 0 — the shim must route everything else to the original routine
- * (list in INTEGRATION.md).
+ * (3,ngw), 1-based.  Implemented variants: Gamma point RKS and LSD (cpb_rhoofr*, cpb_vpsi*), one
+ * k-point at a time without LSD (cpb_*_kpt_dev), meta-GGA tau (cpb_tauofr_dev, cpb_vtaupsi_dev), the
+ * local part of vofrho between the two routines (cpb_vofrho_local*); no LSE, no double grid, akin = 0
+ * — the shim must route everything else to the original routine (list in INTEGRATION.md).
  */
 #ifndef CPB200_H
 #define CPB200_H
