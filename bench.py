@@ -161,14 +161,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_COLLECTIVES_USED = {"mode": None}
+
+
 def _config(args, n_gpus):
     return {"workload": f"BASELINE.json configs[3]: 128 H2O CP-MD, {args.states} states "
                         f"({(args.states + 1) // 2} double-packed FFTs), {args.mesh}^3 mesh, dual 4",
             "mesh": args.mesh, "states": args.states, "pairs_per_batch": args.batch,
             "parallelism": f"cp_groups{n_gpus} (states sharded, rho allreduce, V broadcast)",
-            "collectives": (os.environ.get("CPB_COLLECTIVES", "peer") + (" (cpb_peer_* kernels over NVLink peer memory)"
-                            if os.environ.get("CPB_COLLECTIVES", "peer") == "peer" else " (torch.distributed)"))
-            if n_gpus > 1 else "none",
+            "collectives": {"peer": "peer (cpb_peer_* kernels over NVLink peer memory)", "nccl": "nccl (torch.distributed)",
+                            None: "none", "none": "none"}[_COLLECTIVES_USED["mode"] if n_gpus > 1 else None],
             "l2": "inputs larger than L2 (c0 block + intermediates >> 126 MB per step)"}
 
 
@@ -290,7 +292,14 @@ def run_ours(args, rank, world, local):
     seg = None
     nn = plan.nnr1 + (plan.nnr1 & 1)
     if collectives == "peer":
-        seg = cdist.PeerSegment(2 * nn, rank, world, device=local)
+        try:
+            seg = cdist.PeerSegment(2 * nn, rank, world, device=local)
+        except RuntimeError as e:      # raised on every rank alike: CUDA IPC / peer access unavailable
+            seg = None
+            collectives = "nccl"
+            if rank == 0:
+                print(f"bench.py: peer-memory collectives unavailable ({e}); using torch.distributed", file=sys.stderr)
+    if seg is not None:
         rho = seg.tensor(0, plan.nnr1)
         v = seg.tensor(nn, plan.nnr1)
         v.zero_()
@@ -299,6 +308,7 @@ def run_ours(args, rank, world, local):
     else:
         v = v_host.to(dev) if rank == 0 else torch.zeros(plan.nnr1, dtype=torch.float64, device=dev)
         rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    _COLLECTIVES_USED["mode"] = collectives
     stream = torch.cuda.current_stream()
 
     def redist_and_bcast():

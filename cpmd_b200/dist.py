@@ -137,8 +137,12 @@ class PeerSegment:
         self.n = int(ndoubles) + (int(ndoubles) & 1)
         self._h = C.c_void_p()
         handle = (C.c_ubyte * _lib.CPB_PEER_HANDLE_BYTES)()
-        self._check(self._L.cpb_peer_create(C.byref(self._h), self.device, self.rank, self.world, self.n * 8, handle))
-        mine = bytes(handle)
+        # Every rank takes part in both exchanges even if its own step failed, so that a failure
+        # raises on ALL ranks (the caller may then choose another collective path) instead of
+        # leaving the others blocked in the exchange.
+        rc = self._L.cpb_peer_create(C.byref(self._h), self.device, self.rank, self.world, self.n * 8, handle)
+        err = None if rc == 0 else f"cpb_peer_create: {self._L.cpb_peer_last_error().decode()}"
+        mine = bytes(handle) if rc == 0 else None
         if exchange is None:
             import torch.distributed as dist
 
@@ -147,10 +151,18 @@ class PeerSegment:
                 dist.all_gather_object(out, b, group=group)
                 return out
         blobs = exchange(mine) if self.world > 1 else [mine]
+        if any(b is None for b in blobs):
+            self.close()
+            raise RuntimeError(err or "cpb_peer_create failed on another rank")
         allh = b"".join(blobs)
         assert len(allh) == self.world * _lib.CPB_PEER_HANDLE_BYTES
         buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
-        self._check(self._L.cpb_peer_connect(self._h, buf))
+        rc = self._L.cpb_peer_connect(self._h, buf)
+        err = None if rc == 0 else f"cpb_peer_connect: {self._L.cpb_peer_last_error().decode()}"
+        oks = exchange(b"ok" if rc == 0 else None) if self.world > 1 else [b"ok" if rc == 0 else None]
+        if any(b is None for b in oks):
+            self.close()
+            raise RuntimeError(err or "cpb_peer_connect failed on another rank")
         self.ptr = int(self._L.cpb_peer_local_ptr(self._h))
 
     def _check(self, rc):

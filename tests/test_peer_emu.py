@@ -22,7 +22,9 @@ class _Exchange:
         def ex(b):
             self.slots[rank] = b
             self.bar.wait()
-            return list(self.slots)
+            out = list(self.slots)
+            self.bar.wait()                       # nobody overwrites a slot before everyone copied
+            return out
         return ex
 
 
