@@ -509,6 +509,8 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         from cpmd_b200 import dist as cdist
         cdist.init_from_env()
     run_ours(args, rank, world, local)
