@@ -192,6 +192,9 @@ struct XCfg {
   static constexpr size_t smem_inv(int kcnt) { return (size_t)(SX_ELEMS + N + 2 * kcnt * NA) * sizeof(cplx); }
 };
 
+#ifndef CPB_X_ROT
+#define CPB_X_ROT 1
+#endif
 constexpr uint32_t kNoPW = 0xffffffffu;  // gtab: position holds no plane wave
 constexpr uint32_t kNegPW = 0x80000000u; // gtab: position holds the -G partner of plane wave (value & ~kNegPW)
 
@@ -221,7 +224,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
-  const int slotA = tid % SL, rA = tid / SL;  // slot-major role
+#if CPB_X_ROT
+  // The slot-major pass needs R2 of the max(R1,R2) role rows, i.e. one warp of the block idles in it.
+  // Which physical warp that is depends on the block index, so that the blocks resident on an SM
+  // leave a different sub-partition idle instead of all the same one.
+  const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;
+#else
+  const int tidA = tid;
+#endif
+  const int slotA = tidA % SL, rA = tidA / SL;  // slot-major role
   const int pB = tid % R1, slotB = tid / R1;  // x-major role (valid if slotB < SL)
   const int rayA = blockIdx.x * SL + slotA;
   const int rayB = blockIdx.x * SL + slotB;
@@ -235,8 +246,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
     const int xb = rA + R2 * (KR::lo + j) - pd.xlo;
     tab[j] = (rA < R2 && xb >= 0 && xb < pd.nxb) ? __ldg(&pd.gtab[(size_t)xb * pd.nrp + rayA]) : kNoPW;
     if (rA < R2 && tab[j] == kNoPW) {
-      ST[(0 * KC + j) * NA + tid] = mk(0.0, 0.0);
-      ST[(1 * KC + j) * NA + tid] = mk(0.0, 0.0);
+      ST[(0 * KC + j) * NA + tidA] = mk(0.0, 0.0);
+      ST[(1 * KC + j) * NA + tidA] = mk(0.0, 0.0);
     }
   });
   auto gather = [&](int pair) {
@@ -247,9 +258,9 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
       constexpr int j = decltype(kk)::value;
       if (tab[j] != kNoPW) {
         const uint32_t ig = tab[j] & ~kNegPW;
-        cp_async16(&ST[(0 * KC + j) * NA + tid], c1p + ig);
-        if (s2 >= 0) cp_async16(&ST[(1 * KC + j) * NA + tid], c2p + ig);
-        else ST[(1 * KC + j) * NA + tid] = mk(0.0, 0.0);  // single-state path: c2 = 0
+        cp_async16(&ST[(0 * KC + j) * NA + tidA], c1p + ig);
+        if (s2 >= 0) cp_async16(&ST[(1 * KC + j) * NA + tidA], c2p + ig);
+        else ST[(1 * KC + j) * NA + tidA] = mk(0.0, 0.0);  // single-state path: c2 = 0
       }
     });
     cp_async_commit();
@@ -264,8 +275,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
         constexpr int k = decltype(kk)::value;
         if constexpr (k >= KR::lo && k < KR::hi) {
           constexpr int j = k - KR::lo;
-          const cplx a = ST[(0 * KC + j) * NA + tid];
-          const cplx bq = ST[(1 * KC + j) * NA + tid];
+          const cplx a = ST[(0 * KC + j) * NA + tidA];
+          const cplx bq = ST[(1 * KC + j) * NA + tidA];
           const double sg = (tab[j] & kNegPW) ? -1.0 : 1.0;
           // +G: c1 + i c2 = (a.x - b.y, a.y + b.x);  -G: conj(c1) + i conj(c2) = (a.x + b.y, b.x - a.y)
           v[k] = mk(a.x - sg * bq.y, sg * a.y + bq.x);
@@ -315,7 +326,13 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
-  const int slotA = tid % SL, rA = tid / SL;
+#if CPB_X_ROT
+  constexpr int NTF = XCfg<R1, R2, SL>::NT;
+  const int tidA = (NTF % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NTF / 32))) % NTF) : tid;  // see k_x_inv
+#else
+  const int tidA = tid;
+#endif
+  const int slotA = tidA % SL, rA = tidA / SL;
   const int pB = tid % R1, slotB = tid / R1;
   const int rayA = blockIdx.x * SL + slotA;
   const int rayB = blockIdx.x * SL + slotB;
