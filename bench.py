@@ -83,10 +83,16 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def has_sample(self):
+        try:
+            return self.p is not None and os.path.getsize(self.f.name) > 0
+        except OSError:
+            return False
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
@@ -158,7 +164,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 _COLLECTIVES_USED = {"mode": None}
@@ -354,6 +360,19 @@ def run_ours(args, rank, world, local):
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step_device()
+    # nvidia-smi needs ~0.1-0.3 s before its first sample: keep the GPUs under the same load (untimed
+    # steps, all ranks alike) until the sampler is running, so that short timed regions (N = 8: 5 steps
+    # = 20 ms) still get clock samples taken under load
+    t_pre = time.perf_counter()
+    while True:
+        go = 1.0 if (sampler is None or sampler.has_sample() or time.perf_counter() - t_pre > 3.0) else 0.0
+        if world > 1:
+            flag = torch.tensor([go], dtype=torch.float64, device=dev)
+            dist.broadcast(flag, src=0)
+            go = flag.item()
+        if go:
+            break
+        step_device()
     l0 = plan.launch_count
     ms_step = timed(step_device, args.steps, 0)
     launches = plan.launch_count - l0
@@ -482,7 +501,26 @@ def run_ours(args, rank, world, local):
         line["widened_rows"] = extras
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
+    ignores NCCL_DEBUG_FILE): point fd 1 at stderr for the whole run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -505,6 +543,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
