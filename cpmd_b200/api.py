@@ -322,6 +322,58 @@ class Plan:
                                             _ptr(vtau), ngroups, my_group, 0, _stream_ptr(stream)))
         return c2
 
+    # -- host-array forms of the k-point / meta-GGA entry points (the Fortran drop-in path) ----------
+    def rhoofr_kpt(self, c0, f, wk, hgkp, hgkm, rhoe=None, nstate=None, ngroups=1, my_group=0, accumulate=False):
+        c0 = _as_host(c0, np.complex128)
+        nstate, ld = self._kpt_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        hgkp = np.ascontiguousarray(hgkp, dtype=np.float64)
+        hgkm = np.ascontiguousarray(hgkm, dtype=np.float64)
+        if rhoe is None:
+            rhoe = np.zeros(self.nnr1, dtype=np.float64)
+        rh = _as_host(rhoe, np.float64)
+        out = [C.c_double() for _ in range(3)]
+        flags = _lib.CPB_RHO_ACCUMULATE if accumulate else 0
+        self._check(self._L.cpb_rhoofr_kpt(self._h, c0.ctypes.data, ld, nstate, f.ctypes.data, float(wk),
+                                           hgkp.ctypes.data, hgkm.ctypes.data, ngroups, my_group, rh.ctypes.data,
+                                           *[C.byref(o) for o in out], flags))
+        return (rhoe, *[o.value for o in out])
+
+    def vpsi_kpt(self, c0, c2, f, hgkp, hgkm, vpot, nstate=None, ngroups=1, my_group=0, flags=0):
+        c0 = _as_host(c0, np.complex128)
+        c2h = _as_host(c2, np.complex128)
+        nstate, ld = self._kpt_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        hgkp = np.ascontiguousarray(hgkp, dtype=np.float64)
+        hgkm = np.ascontiguousarray(hgkm, dtype=np.float64)
+        v = _as_host(vpot, np.float64)
+        self._check(self._L.cpb_vpsi_kpt(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data,
+                                         hgkp.ctypes.data, hgkm.ctypes.data, v.ctypes.data, ngroups, my_group, flags))
+        return c2
+
+    def tauofr(self, c0, f, gk, tau=None, nsup=-1, nstate=None, ngroups=1, my_group=0):
+        c0 = _as_host(c0, np.complex128)
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        gk = np.ascontiguousarray(gk, dtype=np.float64)
+        if tau is None:
+            tau = np.empty((2 if nsup >= 0 else 1, self.nnr1), dtype=np.float64)
+        th = _as_host(tau, np.float64)
+        self._check(self._L.cpb_tauofr(self._h, c0.ctypes.data, ld, nstate, f.ctypes.data, int(nsup), gk.ctypes.data,
+                                       ngroups, my_group, th.ctypes.data, 0))
+        return tau
+
+    def vtaupsi(self, c0, c2, f, gk, vtau, nsup=-1, nstate=None, ngroups=1, my_group=0):
+        c0 = _as_host(c0, np.complex128)
+        c2h = _as_host(c2, np.complex128)
+        nstate, ld = self._c0_args(c0, nstate)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        gk = np.ascontiguousarray(gk, dtype=np.float64)
+        vt = _as_host(vtau, np.float64)
+        self._check(self._L.cpb_vtaupsi(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data, int(nsup),
+                                        gk.ctypes.data, vt.ctypes.data, ngroups, my_group, 0))
+        return c2
+
     # -- dense transforms on the density cutoff + local part of vofrho (plan built from nhg) --------
     # Arrays follow the package convention: Fortran (ld, nfields) = C-order (nfields, ld).
     def _dense_shapes(self, f, g):

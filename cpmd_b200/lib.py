@@ -107,6 +107,15 @@ SYMBOLS = {
     "cpb_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "cpb_peer_bcast_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
     "cpb_peer_destroy": (C.c_int, [C.c_void_p]),
+    "cpb_rhoofr_kpt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint]),
+    "cpb_vpsi_kpt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "cpb_tauofr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                             C.c_int, C.c_void_p, C.c_uint]),
+    "cpb_vtaupsi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint]),
     "cpb_tauofr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                  C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
     "cpb_vtaupsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,

@@ -239,6 +239,13 @@ int cpb_rhoofr_kpt_dev(cpb_plan* plan, const void* c0_dev, long ld, int nstate, 
 int cpb_vpsi_kpt_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
                      const double* hgkp_dev, const double* hgkm_dev, const double* vpot_dev, int ngroups,
                      int my_group, unsigned flags, void* stream);
+/* host-pointer forms (what the Fortran shim binds): all arrays in host memory, staged per call */
+int cpb_rhoofr_kpt(cpb_plan* plan, const void* c0, long ld, int nstate, const double* f, double wk,
+                   const double* hgkp, const double* hgkm, int ngroups, int my_group, double* rhoe,
+                   double* ekin, double* rsum_g, double* rsum_r, unsigned flags);
+int cpb_vpsi_kpt(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, const double* f,
+                 const double* hgkp, const double* hgkm, const double* vpot, int ngroups, int my_group,
+                 unsigned flags);
 
 /* ---- cross-group collectives over NVLink peer memory ----------------------------------------
  * One process per GPU (the reference's CP_GROUPS layout, one group per MPI rank).  Each rank
@@ -287,6 +294,11 @@ int cpb_tauofr_dev(cpb_plan* plan, const void* c0_dev, long ld, int nstate, cons
 int cpb_vtaupsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
                     int nsup, const double* gk_dev, const double* vtau_dev, int ngroups, int my_group,
                     unsigned flags, void* stream);
+/* host-pointer forms (what the Fortran shim binds): all arrays in host memory, staged per call */
+int cpb_tauofr(cpb_plan* plan, const void* c0, long ld, int nstate, const double* f, int nsup,
+               const double* gk, int ngroups, int my_group, double* tau, unsigned flags);
+int cpb_vtaupsi(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, const double* f, int nsup,
+                const double* gk, const double* vtau, int ngroups, int my_group, unsigned flags);
 
 /* number of kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 long cpb_plan_launch_count(const cpb_plan* plan);

@@ -554,3 +554,49 @@ def test_empty_and_degenerate_inputs(emu_cdll):
     c2 = np.zeros_like(c0)
     p.vpsi(c0, c2, np.zeros(1), v)                                     # vpsi still acts (fi = 1)
     assert relmax(c2, orc.vpsi(geo, c0, np.zeros_like(c0), np.zeros(1), v, 1.0)) < RTOL
+
+
+def test_host_pointer_forms_of_kpt_and_tau(emu_cdll):
+    """cpb_rhoofr_kpt / cpb_vpsi_kpt / cpb_tauofr / cpb_vtaupsi (host arrays, what the Fortran shim
+    binds): same results as the oracle, groups, ld > rows, LSD, and the Gamma host path afterwards."""
+    geo = orc.make_geometry(20)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=2, _cdll=emu_cdll)
+    ns = 5
+    c0k, fk, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns)
+    ld = 2 * geo.ngw + 3
+    c0p = np.zeros((ns, ld), complex)
+    c0p[:, :2 * geo.ngw] = c0k
+    rho = np.full(geo.nnr1, 9.0)
+    acc_s = np.zeros(2)
+    for g in range(2):                       # two groups accumulate into the same host array
+        _, ek, rg, rr = p.rhoofr_kpt(c0p, fk, 0.4, hgkp, hgkm, rho, ngroups=2, my_group=g, accumulate=(g > 0))
+        acc_s += (ek, rg)
+    ref = orc.rhoofr_kpt(geo, c0k, fk, 0.4, hgkp, hgkm, 1.3, 0.9)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(acc_s[0] - ref["ekin"]) < ETOL and abs(acc_s[1] - ref["rsum_g"]) < ETOL
+    c2 = np.full((ns, ld), 0.5 - 0.25j)
+    c2_ref = orc.vpsi_kpt(geo, c0k, c2[:, :2 * geo.ngw].copy(), fk, hgkp, hgkm, v, 0.9)
+    for g in range(2):
+        p.vpsi_kpt(c0p, c2, fk, hgkp, hgkm, v, ngroups=2, my_group=g)
+    assert relmax(c2[:, :2 * geo.ngw], c2_ref) < RTOL and np.all(c2[:, 2 * geo.ngw:] == 0.5 - 0.25j)
+    # meta-GGA with LSD through the host forms
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    gk = orc.gk_cartesian(geo)
+    for nsup in (None, 2):
+        cs = -1 if nsup is None else nsup
+        nl = 1 if nsup is None else 2
+        ref_t = orc.tauofr(geo, c0, f, gk, 1.3, 0.9, nsup)
+        tau = p.tauofr(c0, f, gk, nsup=cs)
+        assert np.abs(tau - ref_t).max() / np.abs(ref_t).max() < RTOL
+        acc = np.zeros_like(ref_t)
+        for g in range(3):
+            acc += p.tauofr(c0, f, gk, nsup=cs, ngroups=3, my_group=g)
+        assert np.abs(acc - ref_t).max() / np.abs(ref_t).max() < RTOL
+        vt = np.ascontiguousarray(np.stack([v, 0.5 * v[::-1]])[:nl])
+        c2 = 0.3 * c0
+        c2_ref = orc.vtaupsi(geo, c0, c2, f, gk, vt, 0.9, nsup)
+        for g in range(3):
+            p.vtaupsi(c0, c2, f, gk, vt, nsup=cs, ngroups=3, my_group=g)
+        assert relmax(c2, c2_ref) < RTOL
+    # the Gamma host path (shares the staging buffers) still works afterwards
+    rho_g, *_ = p.rhoofr(c0, f)
+    assert relmax(rho_g, orc.rhoofr(geo, c0, f, 1.3, 0.9)["rhoe"]) < RTOL

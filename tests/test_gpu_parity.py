@@ -520,3 +520,28 @@ def test_tau_full_size_properties(dev):
     lhs = -(w * (c0.real * c2.real + c0.imag * c2.imag)).sum().item()
     rhs = (v * tau).sum().item() / nn
     assert abs(lhs - rhs) < ETOL * max(1.0, abs(rhs))
+
+
+def test_host_pointer_forms_of_kpt_and_tau_gpu(dev):
+    """Host-array forms (Fortran drop-in) of the k-point and meta-GGA entry points on the device."""
+    geo = orc.make_geometry(36)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=2)
+    ns = 5
+    c0k, fk, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, ns)
+    rho, ek, rg, rr = p.rhoofr_kpt(c0k, fk, 0.4, hgkp, hgkm)
+    ref = orc.rhoofr_kpt(geo, c0k, fk, 0.4, hgkp, hgkm, 1.3, 0.9)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL and abs(rg - rr) < ETOL
+    c2 = 0.3 * c0k
+    c2_ref = orc.vpsi_kpt(geo, c0k, 0.3 * c0k, fk, hgkp, hgkm, v, 0.9)
+    p.vpsi_kpt(c0k, c2, fk, hgkp, hgkm, v)
+    assert relmax(c2, c2_ref) < RTOL
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    gk = orc.gk_cartesian(geo)
+    ref_t = orc.tauofr(geo, c0, f, gk, 1.3, 0.9, 2)
+    tau = p.tauofr(c0, f, gk, nsup=2)
+    assert np.abs(tau - ref_t).max() / np.abs(ref_t).max() < RTOL
+    vt = np.ascontiguousarray(np.stack([v, 0.5 * v[::-1]]))
+    c2 = 0.3 * c0
+    c2_ref = orc.vtaupsi(geo, c0, c2, f, gk, vt, 0.9, 2)
+    p.vtaupsi(c0, c2, f, gk, vt, nsup=2)
+    assert relmax(c2, c2_ref) < RTOL
