@@ -64,3 +64,28 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
                 assert "libcpb200_emu" not in txt or f == "cpb_defs.h", f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cpb200.h must be consumable by a C compiler (the Fortran shim's iso_c_binding view of it):
+    C99, no C++ constructs, and every declared function must link against the shared library."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    calls = "\n".join(f"  p[{i}] = (void*){name};" for i, name in enumerate(_declared()))
+    src.write_text('#include "cpb200.h"\n#include <stdio.h>\nint main(void) {\n  void* p[%d];\n%s\n'
+                   '  printf("%%s\\n", cpb_version());\n  return p[0] == 0;\n}\n' % (len(_declared()), calls))
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libcpb200.so", f"-Wl,-rpath,{libdir}"])
+    env = dict(os.environ)
+    cuda_lib = "/usr/local/cuda/lib64"
+    env["LD_LIBRARY_PATH"] = cuda_lib + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stderr
