@@ -399,7 +399,8 @@ void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, co
 }
 
 // x pass, forward, in sub-batches of x_sub pairs: k_x_fwd writes the sub-batch's band-ray storage
-// (it stays in L2), k_unpack gathers +G / -G from it and updates c2.
+// (written to and re-read from HBM: it does not stay in L2 at useful sub-batch sizes), k_unpack gathers +G / -G
+// from it and updates c2.
 void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb,
                bool accumulate) {
   cudaStream_t st = w.s;
