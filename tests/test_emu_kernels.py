@@ -600,3 +600,23 @@ def test_host_pointer_forms_of_kpt_and_tau(emu_cdll):
     # the Gamma host path (shares the staging buffers) still works afterwards
     rho_g, *_ = p.rhoofr(c0, f)
     assert relmax(rho_g, orc.rhoofr(geo, c0, f, 1.3, 0.9)["rhoe"]) < RTOL
+
+
+@pytest.mark.parametrize("n,ns", [(16, 3), (20, 4), (24, 5)])
+def test_low_dual_cutoff_runs_unpruned_kernels(emu_cdll, n, ns):
+    """A wavefunction cutoff with dual < 4 (sphere radius 0.45 n): the coefficient band no longer sits in
+    the middle half of the axes, so the plan must select the unpruned (HALF = false) variants of every
+    kernel - including k_z_rho / k_z_vpsi, which the dense-plan tests do not reach."""
+    geo = orc.make_geometry(n, gcutw=(0.45 * n) ** 2)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=2, _cdll=emu_cdll)
+    assert p.info["band_pruned"] == (0, 0, 0)
+    nz, iz = p.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    rho, ek, rg, rr = p.rhoofr(c0, f)
+    ref = orc.rhoofr(geo, c0, f, 1.3, 0.9)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
+    c2 = 0.5 * c0
+    c2_ref = orc.vpsi(geo, c0, c2, f, v, 0.9)
+    p.vpsi(c0, c2, f, v)
+    assert relmax(c2, c2_ref) < RTOL

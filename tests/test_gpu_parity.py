@@ -545,3 +545,17 @@ def test_host_pointer_forms_of_kpt_and_tau_gpu(dev):
     c2_ref = orc.vtaupsi(geo, c0, c2, f, gk, vt, 0.9, 2)
     p.vtaupsi(c0, c2, f, gk, vt, nsup=2)
     assert relmax(c2, c2_ref) < RTOL
+
+
+@pytest.mark.parametrize("n,ns", [(24, 5), (48, 4), (96, 3), (128, 2)])
+def test_low_dual_cutoff_unpruned_kernels_gpu(dev, n, ns):
+    """dual < 4 (sphere radius 0.45 n): every kernel runs its unpruned (HALF = false) instantiation."""
+    geo = orc.make_geometry(n, gcutw=(0.45 * n) ** 2)
+    p = Plan(geo.nr, geo.inyh, geo.hg, 0.9, 1.3, max_batch=2)
+    assert p.info["band_pruned"] == (0, 0, 0)
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    d = dict(c0=c0, f=f, vpot=v)
+    rho, (ek, rg, rr), c2 = _dev_run(p, d, dev)
+    ref = orc.rhoofr(geo, c0, f, 1.3, 0.9)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
+    assert relmax(c2, orc.vpsi(geo, c0, 0.5 * c0, f, v, 0.9)) < RTOL
