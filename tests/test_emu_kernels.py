@@ -620,3 +620,32 @@ def test_low_dual_cutoff_runs_unpruned_kernels(emu_cdll, n, ns):
     c2_ref = orc.vpsi(geo, c0, c2, f, v, 0.9)
     p.vpsi(c0, c2, f, v)
     assert relmax(c2, c2_ref) < RTOL
+
+
+def test_randomised_meshes_cutoffs_and_orders(emu_cdll):
+    """Eight seeded random configurations: anisotropic meshes from the simulator's lengths, cutoff radii
+    between 0.18 and 0.49 of the shortest axis (pruned, mixed and unpruned kernels; planes without rays;
+    ray counts that are not multiples of the x tile), plane waves in a shuffled order (G=0 first),
+    odd state counts, random group splits."""
+    rng = np.random.default_rng(20261017)
+    lengths = [16, 20, 24, 30, 36, 40]
+    for case in range(8):
+        nr = tuple(int(v) for v in rng.choice(lengths, 3))
+        rad = float(rng.uniform(0.18, 0.49)) * min(nr)
+        geo = orc.make_geometry(nr, gcutw=rad * rad)
+        ns = int(rng.integers(1, 6))
+        c0, f, v = orc.synthetic_inputs(geo, ns, seed=case, f_pattern="mixed")
+        perm = np.concatenate([[0], 1 + rng.permutation(geo.ngw - 1)]) if geo.ngw > 1 else np.array([0])
+        p = Plan(nr, geo.inyh[:, perm], geo.hg[perm], 0.9, 1.3, max_batch=int(rng.integers(1, 4)), _cdll=emu_cdll)
+        c0p = np.ascontiguousarray(c0[:, perm])
+        ngroups = int(rng.integers(1, 4))
+        acc = np.zeros(geo.nnr1)
+        c2 = 0.25 * c0p
+        for g in range(ngroups):
+            rho, *_ = p.rhoofr(c0p, f, ngroups=ngroups, my_group=g)
+            acc += rho
+            p.vpsi(c0p, c2, f, v, ngroups=ngroups, my_group=g)
+        ref = orc.rhoofr(geo, c0, f, 1.3, 0.9)
+        tag = f"case {case}: mesh {nr}, radius {rad:.2f}, ngw {geo.ngw}, {ns} states, {ngroups} groups, {p.info['band_pruned']}"
+        assert relmax(acc, ref["rhoe"]) < RTOL, tag
+        assert relmax(c2, orc.vpsi(geo, c0, 0.25 * c0, f, v, 0.9)[:, perm]) < RTOL, tag
