@@ -89,3 +89,28 @@ def test_header_is_plain_c(tmp_path):
     env["LD_LIBRARY_PATH"] = cuda_lib + ":" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "sm_100a" in out.stdout, out.stderr
+
+
+def test_fortran_interface_module_matches_header():
+    """integration/cpb200_interfaces.mod.F90 cannot be compiled here (no Fortran compiler): check
+    mechanically that every BIND(c) interface names a declared symbol and lists the same arguments, in
+    the same order and under the same names, as the C prototype."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "cpb200.h")).read(), flags=re.S)
+    src = open(os.path.join(ROOT, "integration", "cpb200_interfaces.mod.F90")).read()
+    src = re.sub(r"&\s*\n\s*", "", src)                      # join continuation lines
+
+    def c_params(name):
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+        assert m, name
+        body = m.group(1).strip()
+        if body in ("", "void"):
+            return []
+        return [re.findall(r"[A-Za-z_][A-Za-z_0-9]*", p)[-1] for p in body.split(",")]
+
+    found = re.findall(r"FUNCTION\s+\w+\s*\(([^)]*)\)\s*BIND\(c,\s*name='(\w+)'\)", src)
+    assert len(found) >= 20
+    rename = {"seg": "seg", "plan": "plan"}
+    for args, cname in found:
+        f_args = [a.strip() for a in args.split(",") if a.strip()]
+        assert cname in lib.SYMBOLS, cname
+        assert [rename.get(a, a) for a in f_args] == c_params(cname), cname
