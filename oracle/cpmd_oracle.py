@@ -5,11 +5,21 @@ only by ``tests/``, by ``__graft_entry__.smoke()`` and by the ``cpu_baseline`` /
 reference`` legs of ``bench.py``, and always as the *checker*, never as the thing that is shipped
 or measured as the GPU path.
 
-PARITY UNPINNED: the reference tree (/root/reference, CPMD 4.3) ships no golden vectors,
-known-answer tests or fixtures for this path, and it cannot be compiled in the authoring container
-(Fortran 2008 + FFTW + MPI; no Fortran compiler is installed).  This file is therefore a
-restatement of the reference arithmetic, function by function, each citing the reference
-file:line it follows (paths relative to /root/reference/src).  It is pinned instead by the
+PARITY PARTLY PINNED BY REFERENCE CODE.  The reference tree (/root/reference, CPMD 4.3) ships no golden
+vectors, known-answer tests or fixtures for this path, and as a whole it cannot be compiled in the
+authoring container (Fortran 2008 + FFTW + MPI; no Fortran compiler is installed).  One part of the
+path does compile from its own source file: the helper kernels of the reference's cuFFT code path,
+src/cuuser_utils_kernels.cu (set_psi_1/2_states_g, build_density_sum, the pointwise V*psi, phasen,
+putz/getz via MatMov/Zeroing, pack/unpack x2y/y2x).  oracle/Makefile compiles that file for the host
+from where it lies (nothing copied; CPU stand-ins for the few CUDA names in oracle/ref_shim/) into
+oracle/_ref/libcuuser_ref.so, and tests/test_oracle_ref.py (a) compares this file's functions with
+those kernels one by one and (b) assembles fftnew's staged sparse inverse and forward transforms from
+the reference's data-movement kernels plus 1-D DFTs and checks them against the dense transforms used
+below.  That pins the packing rule, the nzhs/indzs and msp index maps as the reference consumes them,
+the z-band insertion, phasen and the density / V*psi formulas.  What remains a restatement, function
+by function with the reference file:line it follows (paths relative to /root/reference/src): the 1-D
+DFT convention of mltfft (sign, scale), the loop structure of vpsi / rhoofr (pairing, occupation
+rules, unpacking at +-G, kinetic term), ppener, the k-point and tau variants.  Those are pinned by the
 known-answer tests derived from the reference's own formulas (tests/test_oracle.py) and by an
 independent second restatement (oracle/staged_oracle.c, which follows ``fftnew``'s staged sparse
 pipeline instead of a dense 3-D FFT).
