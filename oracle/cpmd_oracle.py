@@ -18,7 +18,8 @@ the reference's data-movement kernels plus 1-D DFTs and checks them against the 
 below.  That pins the packing rule, the nzhs/indzs and msp index maps as the reference consumes them,
 the z-band insertion, phasen and the density / V*psi formulas.  What remains a restatement, function
 by function with the reference file:line it follows (paths relative to /root/reference/src): the 1-D
-DFT convention of mltfft (sign, scale), the loop structure of vpsi / rhoofr (pairing, occupation
+DFT itself (its sign/scale convention is the one mltfft_cuda states in code: isign = +1 -> CUFFT_FORWARD,
+-1 -> CUFFT_INVERSE, then zdscal(scale), mltfft_utils.mod.F90:636-646), the loop structure of vpsi / rhoofr (pairing, occupation
 rules, unpacking at +-G, kinetic term), ppener, the k-point and tau variants.  Those are pinned by the
 known-answer tests derived from the reference's own formulas (tests/test_oracle.py) and by an
 independent second restatement (oracle/staged_oracle.c, which follows ``fftnew``'s staged sparse

@@ -31,6 +31,7 @@ def load():
         L.ref_getz.argtypes = [vp, vp, i, i, i, i]
         L.ref_unpack_x2y.argtypes = [vp, vp, i, i, i, ip, i, ip, i, i]
         L.ref_pack_y2x.argtypes = [vp, vp, i, i, i, ip, i, ip, i, i]
+        L.ref_setblock2zero.argtypes = [vp, i, i, i, i, i]
         L.ref_source.restype = C.c_char_p
         _lib = L
     return _lib
@@ -96,6 +97,14 @@ def getz(a, krmin, krmax, kr, m):
     a = np.ascontiguousarray(a, dtype=np.complex128)
     b = np.zeros((krmax - krmin + 1) * m, dtype=np.complex128)
     load().ref_getz(_p(a), _p(b), krmin, krmax, kr, m)
+    return b
+
+
+def setblock2zero(b, trans, n, m, ldbx, ldby):
+    """CuUser_C_SetBlock2Zero(b, transb, n, m, ldbx, ldby): what mltfft_cuda does to its output
+    (mltfft_utils.mod.F90:643-646).  In place on a complex128 array of ldbx*ldby elements."""
+    assert b.dtype == np.complex128 and b.size == ldbx * ldby
+    load().ref_setblock2zero(_p(b), 1 if trans in ("N", "n") else 0, n, m, ldbx, ldby)
     return b
 
 

@@ -100,6 +100,14 @@ void ref_pack_y2x(void* xf, void* yf, int m, int lr1, int lda, int* msp, int lms
   });
 }
 
+// CuUser_C_SetBlock2Zero (cuuser_utils.cu:18-29): mltfft_cuda clears the padding of its output with it
+void ref_setblock2zero(void* a, int trans_is_n, int N, int M, int LDBX, int LDBY) {
+  for_each_thread(LDBX, LDBY, 1, [&] {
+    if (trans_is_n) CuUser_Kernel_SetBlock2Zero((cuDoubleComplex*)a, N, M, LDBX, LDBY);
+    else CuUser_Kernel_SetBlock2Zero((cuDoubleComplex*)a, M, N, LDBX, LDBY);
+  });
+}
+
 const char* ref_source(void) { return REF_KERNELS_CU; }
 
 }  // extern "C"

@@ -5,10 +5,11 @@ pointwise V*psi, phasen, putz/getz, pack/unpack) is compiled for the host from w
 
 What this pins: the packing rule and the nzhs/indzs maps as consumed by the reference's scatter, the
 density and V*psi formulas, phasen's sign pattern, the z-band insertion, and the ray -> plane map
-msp as consumed by the reference's unpack - and, by chaining them with 1-D DFTs in the order and
-with the transpositions of fftnew (fftmain_utils.mod.F90:92-104, 122-136), the whole staged sparse
-transform against the oracle's dense one.  What stays a restatement: the 1-D DFT convention
-(mltfft's sign and scale) and the loop structure of vpsi / rhoofr."""
+msp as consumed by the reference's unpack, the clearing of the padding - and, by chaining them with 1-D
+DFTs in the order and with the transpositions of fftnew (fftmain_utils.mod.F90:92-104, 122-136), the whole
+staged sparse transform against the oracle's dense one.  The 1-D DFT convention is the one the
+reference's GPU path states in code: isign = +1 -> CUFFT_FORWARD, -1 -> CUFFT_INVERSE, then zdscal(scale)
+(mltfft_utils.mod.F90:636-646).  What stays a restatement: the loop structure of vpsi / rhoofr."""
 import numpy as np
 import pytest
 
@@ -64,23 +65,25 @@ def test_phasen_matches_reference_kernel(geo):
 
 
 def _mltfft_nt(a, ldax, n, m, inverse, scale=1.0):
-    """mltfft('N','T',a,ldax,m,b,m,ldax,n,m,isign,scale) as fftnew's inverse branch uses it
-    (mltfft_utils.mod.F90:40-256): a(ldax, m), m transforms of length n along the first index, output
-    transposed b(m, ldax) with the rows n+1..ldax zero.  isign = -1 is the unnormalised e^{+i...}."""
+    """mltfft('N','T',a,ldax,m,b,m,ldax,n,m,isign,scale) the way the reference's GPU path defines it
+    (mltfft_cuda, mltfft_utils.mod.F90:612-655): a batched Z2Z DFT - isign = +1 -> CUFFT_FORWARD
+    (e^{-i...}), otherwise CUFFT_INVERSE (e^{+i...}, unnormalised) (:636-641) - of the m columns a(1:n, j),
+    written transposed to b(j, 1:n), then scaled (:644) and its padding cleared by the reference's own
+    SetBlock2Zero kernel (:645).  The padding of b is filled with garbage first to see that kernel work."""
     a2 = a.reshape(m, ldax)[:, :n]                            # [transform j][element]
     t = (np.fft.ifft(a2, axis=1) * n) if inverse else np.fft.fft(a2, axis=1)
-    b = np.zeros((ldax, m), dtype=np.complex128)              # b(j, k) -> flat k*m + j
+    b = np.full((ldax, m), 9.0 - 9.0j)                        # b(j, k) -> flat k*m + j
     b[:n, :] = (t * scale).T
-    return b.reshape(-1)
+    return ref.setblock2zero(b.reshape(-1), "T", n, m, m, ldax)
 
 
 def _mltfft_tn(a, ldbx, n, m, scale=1.0):
     """mltfft('T','N',a,m,ldbx,b,ldbx,m,n,m,isign=+1,scale): input transposed a(m, ldbx), output b(ldbx, m)."""
     a2 = a.reshape(ldbx, m)[:n, :].T
     t = np.fft.fft(a2, axis=1) * scale
-    b = np.zeros((m, ldbx), dtype=np.complex128)
+    b = np.full((m, ldbx), 9.0 - 9.0j)
     b[:, :n] = t
-    return b.reshape(-1)
+    return ref.setblock2zero(b.reshape(-1), "N", n, m, ldbx, m)
 
 
 def test_staged_sparse_transforms_through_reference_kernels(geo):
