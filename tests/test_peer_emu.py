@@ -50,7 +50,7 @@ def _run(world, fn):
     assert not err, err
 
 
-@pytest.mark.parametrize("world,n", [(2, 1000), (3, 4098), (4, 17 * 17 * 17 + 1), (8, 50)])
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 4098), (4, 17 * 17 * 17 + 1), (5, 14), (8, 50), (16, 300)])
 def test_allreduce_and_bcast_threads_as_ranks(emu_cdll, world, n):
     n += n & 1
     rng = np.random.default_rng(world)
