@@ -18,6 +18,13 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
+        if not os.path.exists(PATH) and os.path.exists("/root/reference/src/cuuser_utils_kernels.cu"):
+            # authoring container: build on demand (the GPU box has no /root/reference and uses the
+            # prebuilt file that travels with the snapshot)
+            import subprocess
+            env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+            subprocess.call(["make", "-C", _HERE, "_ref/libcuuser_ref.so"], env=env, stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL)
         if not os.path.exists(PATH):
             return None
         L = C.CDLL(PATH)
