@@ -117,3 +117,47 @@ def test_staged_sparse_transforms_through_reference_kernels(geo):
     g = _mltfft_tn(xf, kr1, n1, geo.nrays, 1.0 / (n1 * n2 * n3))                      # (qr1s, nrays)
     want_g = orc.fwfftn_sparse(geo, v * want)
     assert np.abs(g - want_g).max() < 1e-12 * np.abs(want_g).max()
+
+
+def test_dense_transforms_through_reference_kernels():
+    """The dense branch of fftnew (fftmain_utils.mod.F90:105-120, 137-153) on the density-cutoff sphere,
+    assembled from the reference's unpack/pack + phasen kernels and 1-D DFTs, against the oracle's
+    invfftn_dense / fwfftn_dense (what cpb_vofrho_local is compared with).  msqf = y + (z-1)*kr2s
+    (fftprp_utils.mod.F90:259-268, full set) is derived here from the ray table."""
+    geo = orc.make_density_geometry((16, 20, 24))
+    n1, n2, n3 = geo.nr
+    kr1, kr2, kr3 = geo.kr
+    yy, zz = np.nonzero(geo.mg)                                   # 0-based (y, z) of every ray
+    msqf = np.zeros(geo.nrays, dtype=np.int32)
+    msqf[geo.mg[yy, zz] - 1] = (yy + 1) + zz * kr2
+    sp8 = np.array([geo.nrays], dtype=np.int32)
+    L = ref.load()
+    rng = np.random.default_rng(4)
+    vg = (rng.standard_normal(geo.ngw) + 1j * rng.standard_normal(geo.ngw)) * np.exp(-geo.hg / 30)
+    vg[0] = vg[0].real
+    v = np.zeros(kr1 * geo.nrays, complex)                        # vofrhob_utils.mod.F90:155-173
+    v[geo.indzs - 1] = np.conj(vg)
+    v[geo.nzhs - 1] = vg
+    # ---- inverse: x, unpack (full planes), y, z, phasen
+    xf = _mltfft_nt(v, kr1, n1, geo.nrays, True)
+    mm = kr2 * kr3
+    yf = np.zeros(mm * kr1, complex)
+    L.ref_unpack_x2y(xf.ctypes.data, yf.ctypes.data, mm, kr1, geo.nrays * kr1, msqf.ctypes.data, geo.nrays,
+                     sp8.ctypes.data, 0, 1)
+    xf = _mltfft_nt(yf, kr2, n2, kr3 * kr1, True)                 # [y][x][z]
+    out = _mltfft_nt(xf, kr3, n3, kr1 * kr2, True)                # [z][y][x]
+    out = ref.phasen(geo, out)
+    want = orc.invfftn_dense(geo, v)
+    assert np.abs(out - want).max() < 1e-12 * np.abs(want).max()
+    assert np.abs(out.imag).max() < 1e-12 * np.abs(want).max()    # a real potential
+    # ---- forward: phasen, z, y, pack, x with the 1/N scale
+    rho = out.real.copy()
+    f = ref.phasen(geo, rho.astype(complex))
+    xf = _mltfft_tn(f, kr3, n3, kr1 * kr2)                        # [jj][z]
+    yf = _mltfft_tn(xf, kr2, n2, kr3 * kr1)                       # [x][z][y]
+    xr = np.zeros(geo.nrays * kr1, complex)
+    L.ref_pack_y2x(xr.ctypes.data, yf.ctypes.data, mm, kr1, geo.nrays * kr1, msqf.ctypes.data, geo.nrays,
+                   sp8.ctypes.data, 0, 1)
+    g = _mltfft_tn(xr, kr1, n1, geo.nrays, 1.0 / (n1 * n2 * n3))
+    assert np.abs(g - orc.fwfftn_dense(geo, rho)).max() < 1e-13
+    assert np.abs(g[geo.nzhs - 1] - vg).max() < 1e-12             # round trip on the sphere
