@@ -262,7 +262,8 @@ int cpb_vpsi_kpt(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, 
  * of calls.  cpb_peer_allreduce_f64 / cpb_peer_bcast_f64 only ENQUEUE their kernels on `stream` (later
  * work on the same stream sees the result); cpb_peer_barrier and cpb_peer_check synchronise the stream
  * and return CPB_ERR_CUDA if a rank failed to show up at a barrier within ~2 s (the kernels give up
- * instead of hanging the device). */
+ * instead of hanging the device).  cpb_peer_destroy unmaps the peers and frees the own segment: call
+ * it only after every rank has passed a final cpb_peer_barrier (a peer may otherwise still be reading). */
 #define CPB_PEER_HANDLE_BYTES 64
 typedef struct cpb_peer cpb_peer;
 const char* cpb_peer_last_error(void);
