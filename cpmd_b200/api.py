@@ -59,6 +59,10 @@ def _is_torch(a):
     return not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
 
 
+def _numel(a):
+    return a.numel() if _is_torch(a) else np.asarray(a).size
+
+
 class Plan:
     """One FFT/G-vector plan on one GPU (``cpb_plan_create``)."""
 
@@ -121,6 +125,12 @@ class Plan:
     def launch_count(self):
         return int(self._L.cpb_plan_launch_count(self._h))
 
+    def set_vpot_event(self, event):
+        """One-shot: the next ``vpsi*_dev`` call waits for ``event`` (torch.cuda.Event recorded on the
+        stream that produces vpot, or a raw cudaEvent_t) only before its first z pass."""
+        h = None if event is None else (event if isinstance(event, int) else event.cuda_event)
+        self._check(self._L.cpb_plan_set_vpot_event(self._h, C.c_void_p(h) if h is not None else None))
+
     def set_profiling(self, on=True):
         self._check(self._L.cpb_plan_set_profiling(self._h, int(bool(on))))
 
@@ -144,7 +154,30 @@ class Plan:
             nstate = ns
         if nstate > ns or ld < self.ngw:
             raise ValueError("c0 shape inconsistent with nstate/ngw")
+        if _is_torch(c0) and not c0.is_contiguous():
+            raise ValueError("c0 must be contiguous")
         return int(nstate), int(ld)
+
+    @staticmethod
+    def _f_arg(f, nstate):
+        """occupations as a contiguous float64 host array with at least nstate entries (the C side
+        indexes f[0 .. nstate))"""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        if f.ndim != 1 or f.shape[0] < nstate:
+            raise ValueError(f"f must hold at least nstate = {nstate} occupations")
+        return f
+
+    def _g_arg(self, a, name, per=1):
+        """a per-plane-wave real array (hgkp, hgkm: ngw; gk: 3*ngw) - host or device; None is passed
+        on as NULL (the C side rejects it)"""
+        if a is None:
+            return a
+        n = a.numel() if _is_torch(a) else np.asarray(a).size
+        if n < per * self.ngw:
+            raise ValueError(f"{name} must hold at least {per}*ngw = {per * self.ngw} doubles")
+        if _is_torch(a) and not a.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+        return a
 
     # -- host-array entry points (the Fortran drop-in path) --------------------------------
     def rhoofr(self, c0, f, rhoe=None, nstate=None, ngroups=1, my_group=0, flags=0):
@@ -152,7 +185,7 @@ class Plan:
         (rhoe, ekin, rsum_g, rsum_r); rhoe is written into the given array if supplied."""
         c0 = _as_host(c0, np.complex128)
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         if rhoe is None:
             rhoe = np.empty(self.nnr1, dtype=np.float64)
         rh = _as_host(rhoe, np.float64)
@@ -171,7 +204,7 @@ class Plan:
         if c2h.shape != c0.shape:
             raise ValueError("c2 must have the shape of c0")
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         v = _as_host(vpot, np.float64)
         if v.size < self.nnr1:
             raise ValueError("vpot too small")
@@ -185,7 +218,7 @@ class Plan:
         """``cpb_rhoofr_lsd`` (host arrays).  Returns (rhoe, ekin, rsum_g, rsum_r, csums, csumsabs)."""
         c0 = _as_host(c0, np.complex128)
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         if rhoe is None:
             rhoe = np.empty((2, self.nnr1), dtype=np.float64)
         rh = _as_host(rhoe, np.float64)
@@ -204,7 +237,7 @@ class Plan:
         if c2h.shape != c0.shape:
             raise ValueError("c2 must have the shape of c0")
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         v = _as_host(vpot, np.float64)
         if v.size < 2 * self.nnr1:
             raise ValueError("vpot too small (needs two columns)")
@@ -215,7 +248,7 @@ class Plan:
 
     def rhoofr_lsd_dev(self, c0, f, nsup, rhoe, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         if rhoe.numel() < 2 * self.nnr1:
             raise ValueError("rhoe too small (needs two columns)")
         out = [C.c_double() for _ in range(5)]
@@ -226,7 +259,7 @@ class Plan:
 
     def vpsi_lsd_dev(self, c0, c2, f, nsup, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         if vpot.numel() < 2 * self.nnr1:
             raise ValueError("vpot too small (needs two columns)")
         rc = self._L.cpb_vpsi_lsd_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, int(nsup), _ptr(vpot),
@@ -253,7 +286,7 @@ class Plan:
         """``cpb_rhoofr_dev``: c0 (nstate, ld) complex128 CUDA tensor, rhoe float64 CUDA tensor of
         nnr1 elements (overwritten).  Returns (ekin, rsum_g, rsum_r) of the group's block."""
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         if rhoe.numel() < self.nnr1:
             raise ValueError("rhoe too small")
         ekin, rg, rr = C.c_double(), C.c_double(), C.c_double()
@@ -265,7 +298,9 @@ class Plan:
 
     def vpsi_dev(self, c0, c2, f, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        if tuple(c2.shape) != tuple(c0.shape) or _numel(vpot) < self.nnr1:
+            raise ValueError("c2 must have the shape of c0 and vpot nnr1 entries")
         rc = self._L.cpb_vpsi_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, _ptr(vpot),
                                   ngroups, my_group, flags, _stream_ptr(stream))
         self._check(rc)
@@ -273,6 +308,8 @@ class Plan:
 
     # -- k-points (tkpts%tkpnt): c0/c2 (nstate, ld >= 2 ngw) CUDA tensors, one k-point per call ------
     def _kpt_args(self, c0, nstate):
+        if c0.ndim != 2:
+            raise ValueError("c0 must be (nstate, ld)")
         ns, ld = c0.shape
         if nstate is None:
             nstate = ns
@@ -285,7 +322,10 @@ class Plan:
         """``cpb_rhoofr_kpt_dev``: one k-point of rhoofr_c (rhoofr_c_utils.mod.F90:117-178).
         Returns (ekin, rsum_g, rsum_r) contributions."""
         nstate, ld = self._kpt_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        self._g_arg(hgkp, "hgkp"), self._g_arg(hgkm, "hgkm")
+        if _numel(rhoe) < self.nnr1:
+            raise ValueError("rhoe too small")
         out = [C.c_double() for _ in range(3)]
         flags = _lib.CPB_RHO_ACCUMULATE if accumulate else 0
         self._check(self._L.cpb_rhoofr_kpt_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, float(wk), _ptr(hgkp),
@@ -296,7 +336,10 @@ class Plan:
     def vpsi_kpt_dev(self, c0, c2, f, hgkp, hgkm, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
         """``cpb_vpsi_kpt_dev``: vpsi's k-point branch for one k-point (vpsi_utils.mod.F90:562-625)."""
         nstate, ld = self._kpt_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        self._g_arg(hgkp, "hgkp"), self._g_arg(hgkm, "hgkm")
+        if tuple(c2.shape) != tuple(c0.shape) or _numel(vpot) < self.nnr1:
+            raise ValueError("c2 must have the shape of c0 and vpot nnr1 entries")
         self._check(self._L.cpb_vpsi_kpt_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, _ptr(hgkp),
                                              _ptr(hgkm), _ptr(vpot), ngroups, my_group, flags, _stream_ptr(stream)))
         return c2
@@ -306,10 +349,11 @@ class Plan:
         """``cpb_tauofr_dev``: tau (nnr1,) or (2, nnr1) with LSD, zeroed and written
         (tauofr_utils.mod.F90:42-111)."""
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
         need = (2 if nsup >= 0 else 1) * self.nnr1
         if (tau.numel() if _is_torch(tau) else tau.size) < need:
             raise ValueError("tau too small")
+        self._g_arg(gk, "gk", 3)
         self._check(self._L.cpb_tauofr_dev(self._h, _ptr(c0), ld, nstate, f.ctypes.data, int(nsup), _ptr(gk), ngroups,
                                            my_group, _ptr(tau), 0, _stream_ptr(stream)))
         return tau
@@ -317,7 +361,10 @@ class Plan:
     def vtaupsi_dev(self, c0, c2, f, gk, vtau, nsup=-1, nstate=None, ngroups=1, my_group=0, stream=None):
         """``cpb_vtaupsi_dev``: c2 -= ... (vtaupsi_utils.mod.F90:38-165); vtau (nnr1,) or (2, nnr1)."""
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        self._g_arg(gk, "gk", 3)
+        if tuple(c2.shape) != tuple(c0.shape) or _numel(vtau) < (2 if nsup >= 0 else 1) * self.nnr1:
+            raise ValueError("c2 must have the shape of c0 and vtau nnr1 (2*nnr1 with LSD) entries")
         self._check(self._L.cpb_vtaupsi_dev(self._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, int(nsup), _ptr(gk),
                                             _ptr(vtau), ngroups, my_group, 0, _stream_ptr(stream)))
         return c2
@@ -326,9 +373,9 @@ class Plan:
     def rhoofr_kpt(self, c0, f, wk, hgkp, hgkm, rhoe=None, nstate=None, ngroups=1, my_group=0, accumulate=False):
         c0 = _as_host(c0, np.complex128)
         nstate, ld = self._kpt_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
-        hgkp = np.ascontiguousarray(hgkp, dtype=np.float64)
-        hgkm = np.ascontiguousarray(hgkm, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        hgkp = self._g_arg(np.ascontiguousarray(hgkp, dtype=np.float64), 'hgkp')
+        hgkm = self._g_arg(np.ascontiguousarray(hgkm, dtype=np.float64), 'hgkm')
         if rhoe is None:
             rhoe = np.zeros(self.nnr1, dtype=np.float64)
         rh = _as_host(rhoe, np.float64)
@@ -343,9 +390,9 @@ class Plan:
         c0 = _as_host(c0, np.complex128)
         c2h = _as_host(c2, np.complex128)
         nstate, ld = self._kpt_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
-        hgkp = np.ascontiguousarray(hgkp, dtype=np.float64)
-        hgkm = np.ascontiguousarray(hgkm, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        hgkp = self._g_arg(np.ascontiguousarray(hgkp, dtype=np.float64), 'hgkp')
+        hgkm = self._g_arg(np.ascontiguousarray(hgkm, dtype=np.float64), 'hgkm')
         v = _as_host(vpot, np.float64)
         self._check(self._L.cpb_vpsi_kpt(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data,
                                          hgkp.ctypes.data, hgkm.ctypes.data, v.ctypes.data, ngroups, my_group, flags))
@@ -354,8 +401,8 @@ class Plan:
     def tauofr(self, c0, f, gk, tau=None, nsup=-1, nstate=None, ngroups=1, my_group=0):
         c0 = _as_host(c0, np.complex128)
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
-        gk = np.ascontiguousarray(gk, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        gk = self._g_arg(np.ascontiguousarray(gk, dtype=np.float64), 'gk', 3)
         if tau is None:
             tau = np.empty((2 if nsup >= 0 else 1, self.nnr1), dtype=np.float64)
         th = _as_host(tau, np.float64)
@@ -367,8 +414,8 @@ class Plan:
         c0 = _as_host(c0, np.complex128)
         c2h = _as_host(c2, np.complex128)
         nstate, ld = self._c0_args(c0, nstate)
-        f = np.ascontiguousarray(f, dtype=np.float64)
-        gk = np.ascontiguousarray(gk, dtype=np.float64)
+        f = self._f_arg(f, nstate)
+        gk = self._g_arg(np.ascontiguousarray(gk, dtype=np.float64), 'gk', 3)
         vt = _as_host(vtau, np.float64)
         self._check(self._L.cpb_vtaupsi(self._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data, int(nsup),
                                         gk.ctypes.data, vt.ctypes.data, ngroups, my_group, 0))

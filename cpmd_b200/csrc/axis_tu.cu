@@ -2,6 +2,7 @@
 // Instantiates the six pipeline kernels for N = R1*R2 and exports their launchers.
 #include <map>
 #include <mutex>
+#include <utility>
 
 #include "axis.h"
 #include "rt.h"
@@ -18,14 +19,17 @@ constexpr int R1 = CPB_R1, R2 = CPB_R2, N = CPB_N, B = CPB_B, SL = CPB_SL;
 constexpr int RM = R1 > R2 ? R1 : R2;
 
 // opt in to more than the default 48 KB (static + dynamic); the size may depend on the plan (band
-// width), so remember the largest value set per kernel
+// width), so remember the largest value set per (device, kernel): the attribute belongs to the
+// device that is current when it is set, and one process may hold plans on several devices
 template <class K>
 void allow_smem(K kern, size_t bytes) {
 #if !defined(CPB_EMULATE)
   static std::mutex mu;
-  static std::map<const void*, size_t> set;  // per kernel instantiation
+  static std::map<std::pair<int, const void*>, size_t> set;  // per device and kernel instantiation
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) throw Error(-2, "cudaGetDevice failed");
   std::lock_guard<std::mutex> lock(mu);
-  size_t& cur = set[reinterpret_cast<const void*>(kern)];
+  size_t& cur = set[std::make_pair(dev, reinterpret_cast<const void*>(kern))];
   if (bytes > cur) {
     if (bytes > 227 * 1024) throw Error(-4, "kernel needs more shared memory than an SM has (mesh too large)");
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)

@@ -137,6 +137,7 @@ struct cpb_plan {
   };
   static constexpr int kNumWS = 2;
   WorkSpace ws[kNumWS];
+  rt::event_t vpot_event = nullptr;  // one-shot: the next vpsi waits for it before its first z pass
   int nws = 1;  // work spaces in use (default 1: on B200 the overlap costs vpsi more than it gains; CPB_STREAMS=2)
   rt::event_t ev_fork = nullptr;
   size_t workspace_bytes = 0;
@@ -544,6 +545,8 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr
   const std::vector<BatchSpan> batches = make_batches(p, np, n0);
   const int nbatches = (int)batches.size();
   fork_streams(p, st, nbatches);
+  rt::event_t vready = p->vpot_event;  // cpb_plan_set_vpot_event: only the z passes read vpot
+  p->vpot_event = nullptr;
   for (int b = 0; b < nbatches; ++b) {
     const int off = batches[b].off, nb = batches[b].n;
     const double* vpot = batches[b].chan ? v1 : v0;
@@ -556,6 +559,7 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr
       const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm);
       cplx* T2 = reuse ? reuse + (size_t)off * p->t2_pair : w.T2;
       if (!reuse) { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
+      if (vready && b < p->nws && xt0 == 0) rt::stream_wait(w.s, vready);  // first z pass of every work-space stream
       { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
       { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
     }
@@ -991,6 +995,12 @@ int cpb_plan_set_streams(cpb_plan* p, int n) {
   for (const auto& w : p->ws) have += (w.T1 != nullptr);
   if (n < 1 || n > have) return fail(CPB_ERR_INVALID, "stream count outside 1..allocated work spaces");
   p->nws = n;
+  return CPB_OK;
+}
+
+int cpb_plan_set_vpot_event(cpb_plan* p, void* event) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  p->vpot_event = (rt::event_t)event;
   return CPB_OK;
 }
 

@@ -12,10 +12,11 @@
 // (fftcu_methods.mod.F90).  Intermediates:
 //   T1[pair][xt][ray][B]       after the x pass, only rays inside the cutoff disc (S_x bytes/pair);
 //                              xt = x tile of B consecutive x (B*16 = 128-byte rows)
-//   T2[pair][xtc][y][zr][B]    after the y pass, only z planes inside the band (S_y bytes/pair),
-//                              held for ONE CHUNK of x tiles at a time (xtc = xt - xt0): the y and z
-//                              passes of a chunk run back to back and the chunk buffer is reused, so
-//                              it stays resident in the 126 MB L2 and never travels to HBM.
+//   T2[pair][xtc][y][zr][B]    after the y pass, only z planes inside the band (S_y bytes/pair).  By
+//                              default it holds ALL x tiles of the batch and goes through HBM once in
+//                              each direction (measured: ncu DRAM bytes = the algorithmic S_y, see
+//                              profiles/*_traffic.json); CPB_CHUNK_XT splits the y/z passes into chunks
+//                              of x tiles (xtc = xt - xt0), a tuning hook that did not pay off.
 // The full n^3 complex box never exists in memory: the z pass consumes it in registers.
 //
 // Every 1-D FFT is a two-pass Cooley-Tukey N = RA*RB: each thread owns one radix-RA

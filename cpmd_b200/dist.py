@@ -164,6 +164,7 @@ class PeerSegment:
             self.close()
             raise RuntimeError(err or "cpb_peer_connect failed on another rank")
         self.ptr = int(self._L.cpb_peer_local_ptr(self._h))
+        self._views = []          # weak references to the tensors handed out by tensor()
 
     def _check(self, rc):
         if rc != 0:
@@ -173,9 +174,13 @@ class PeerSegment:
         """float64 CUDA tensor over doubles [offset, offset+n) of the local segment."""
         import torch
 
+        import weakref
+
         if offset < 0 or offset + n > self.n:
             raise ValueError("range outside the segment")
-        return torch.as_tensor(_DevArray(self.ptr + 8 * offset, n, self), device=torch.device("cuda", self.device))
+        t = torch.as_tensor(_DevArray(self.ptr + 8 * offset, n, self), device=torch.device("cuda", self.device))
+        self._views.append(weakref.ref(t))
+        return t
 
     def numpy(self, offset, n):
         """Host view (kernel simulator only: its "device" memory is host memory)."""
@@ -198,6 +203,30 @@ class PeerSegment:
     def bcast(self, offset, n, src=0, stream=None):
         self._check(self._L.cpb_peer_bcast_f64(self._h, int(offset), int(n), int(src), self._sp(stream)))
 
+    def allgather(self, offset, counts, stream=None):
+        """In place: block q (counts[q] doubles, back to back from ``offset``) of rank q to every rank."""
+        import ctypes as C
+        if len(counts) != self.world:
+            raise ValueError("one count per rank")
+        arr = (C.c_size_t * self.world)(*[int(c) for c in counts])
+        self._check(self._L.cpb_peer_allgather_f64(self._h, int(offset), arr, self._sp(stream)))
+
+    def redist_c2(self, offset, ld, nstate, stream=None):
+        """cp_grp_redist(C2_vpsi) (vpsi_utils.mod.F90:708-712): all-gather of the part_1d state blocks of
+        the (nstate, ld) complex128 array that starts ``offset`` doubles into the segment."""
+        self._check(self._L.cpb_peer_redist_c2(self._h, int(offset), int(ld), int(nstate), self._sp(stream)))
+
+    def allreduce_scalars(self, vals, stream=None):
+        """Sum of up to 8 host doubles over the ranks, in rank order (ekin, rsum_g, rsum_r)."""
+        import ctypes as C
+        vals = [float(v) for v in vals]
+        arr = (C.c_double * len(vals))(*vals)
+        self._check(self._L.cpb_peer_allreduce_scalars(self._h, arr, len(vals), self._sp(stream)))
+        return list(arr)
+
+    def set_timeout_ms(self, ms):
+        self._check(self._L.cpb_peer_set_timeout_ms(self._h, float(ms)))
+
     def barrier(self, stream=None):
         self._check(self._L.cpb_peer_barrier(self._h, self._sp(stream)))
 
@@ -205,13 +234,21 @@ class PeerSegment:
         """Synchronise the stream and raise if a barrier of an earlier collective timed out."""
         self._check(self._L.cpb_peer_check(self._h, self._sp(stream)))
 
-    def close(self):
+    def close(self, force=False):
+        """Unmap the peers and free the own segment.  Refuses while tensors handed out by :meth:`tensor`
+        are still referenced (they would dangle) unless ``force``."""
         if getattr(self, "_h", None) is not None and self._h.value:
+            alive = [r for r in getattr(self, "_views", []) if r() is not None]
+            if alive and not force:
+                raise RuntimeError(f"PeerSegment.close(): {len(alive)} tensor view(s) of the segment are still "
+                                   "alive; delete them first (or close(force=True))")
             self._L.cpb_peer_destroy(self._h)
             self._h = None
 
     def __del__(self):
+        # a tensor view keeps the segment alive (its array interface owns a reference), so by the time
+        # the segment is collected no view is left
         try:
-            self.close()
+            self.close(force=True)
         except Exception:
             pass

@@ -106,6 +106,10 @@ SYMBOLS = {
     "cpb_peer_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpb_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "cpb_peer_bcast_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
+    "cpb_peer_allgather_f64": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
+    "cpb_peer_redist_c2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_long, C.c_int, C.c_void_p]),
+    "cpb_peer_allreduce_scalars": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_void_p]),
+    "cpb_peer_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_double]),
     "cpb_peer_destroy": (C.c_int, [C.c_void_p]),
     "cpb_rhoofr_kpt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double),
@@ -121,6 +125,7 @@ SYMBOLS = {
     "cpb_vtaupsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
+    "cpb_plan_set_vpot_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),

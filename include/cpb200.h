@@ -90,7 +90,7 @@ typedef struct {
   int radix[3][2];    /* two-pass factorisation of each axis */
   size_t workspace_bytes;
   int band_pruned[3]; /* 1: the axis runs the band-pruned kernel variants (coefficients in the middle half) */
-  int chunk_xtiles;   /* x tiles (of 8 columns) per y/z chunk; the chunk's intermediate stays in L2 */
+  int chunk_xtiles;   /* x tiles (of 8 columns) per y/z chunk (default: all of them, one y and one z launch per batch) */
   int streams;        /* work spaces / streams the batches of a call alternate between */
 } cpb_plan_info;
 
@@ -178,6 +178,13 @@ int cpb_vpsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int 
                  const double* f, const double* vpot_dev, int ngroups, int my_group,
                  unsigned flags, void* stream);
 
+/* One-shot ordering hint for the next cpb_vpsi*_dev call: `event` (a cudaEvent_t the caller recorded on
+ * the stream that PRODUCES vpot, e.g. the stream of cpb_peer_bcast_f64 or of the caller's vofrho) is
+ * waited for only before the first kernel that reads vpot - the z pass of the first batch - so the
+ * gather and the x / y passes of that batch overlap the producer instead of queueing behind it.  Without
+ * it the caller orders the whole call after the producer as usual.  NULL clears a pending hint. */
+int cpb_plan_set_vpot_event(cpb_plan* plan, void* event);
+
 /* ---- dense transforms on the density cutoff and the local part of vofrho -------------------
  * (the step between rhoofr and vpsi.)  These run on a plan created by cpb_plan_create
  * from the nhg vectors of the DENSITY cutoff: ngw := ncpw%nhg, inyh(3,nhg), hg(nhg) - the same
@@ -258,12 +265,28 @@ int cpb_vpsi_kpt(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, 
  *                           cp_grp_utils.mod.F90:98-120).  Deterministic (fixed rank order): all
  *                           ranks end with bit-identical data.
  *   cpb_peer_bcast_f64      rank `src`'s array to every rank (V(r) once per step).
- * offset / n are in doubles and even.  Calls are collective: every rank must make the same sequence
- * of calls.  cpb_peer_allreduce_f64 / cpb_peer_bcast_f64 only ENQUEUE their kernels on `stream` (later
- * work on the same stream sees the result); cpb_peer_barrier and cpb_peer_check synchronise the stream
- * and return CPB_ERR_CUDA if a rank failed to show up at a barrier within ~2 s (the kernels give up
- * instead of hanging the device).  cpb_peer_destroy unmaps the peers and frees the own segment: call
- * it only after every rank has passed a final cpb_peer_barrier (a peer may otherwise still be reading). */
+ *   cpb_peer_allgather_f64  in place: block q (counts[q] doubles; the blocks lie back to back from
+ *                           `offset` on) is valid on rank q on entry and on every rank on return.
+ *   cpb_peer_redist_c2      cp_grp_redist(C2_vpsi) of a device-resident run (vpsi_utils.mod.F90:708-712,
+ *                           forces_driver.mod.F90:283): the reference sums zero-padded full C2 arrays over
+ *                           the groups, which is an all-gather of the owned state blocks.  The (ld, nstate)
+ *                           COMPLEX*16 array starts `offset` doubles into the segment; the blocks are the
+ *                           part_1d blocks of the ranks (part_1d.mod.F90:22-57).
+ *   cpb_peer_allreduce_scalars  n <= 8 host doubles summed over the ranks in rank order (the group-partial
+ *                           ekin / rsum_g / rsum_r of cpb_rhoofr_dev; the reference computes them redundantly
+ *                           on every group, rhoofr_utils.mod.F90:178).  Synchronises the stream.
+ * offset / n / counts are in doubles and even.  Calls are collective: every rank must make the same
+ * sequence of calls.  cpb_peer_allreduce_f64 / cpb_peer_bcast_f64 / cpb_peer_allgather_f64 only ENQUEUE
+ * their kernels on `stream` (later work on the same stream sees the result).  A rank that fails to show
+ * up at a barrier within the timeout (cpb_peer_set_timeout_ms; default 20 s, or CPB_PEER_TIMEOUT_MS in
+ * the environment) does not hang the device: the waiting ranks raise a sticky error word in EVERY
+ * segment, every later collective kernel of the segment leaves its data untouched, and the segment is
+ * unusable from then on.  The error is reported by the synchronising calls - cpb_peer_barrier,
+ * cpb_peer_allreduce_scalars and cpb_peer_check return CPB_ERR_CUDA - so a caller MUST call
+ * cpb_peer_check (or one of the other two) after the collectives of a step before it trusts the data.
+ * cpb_peer_destroy unmaps the peers and frees the own segment: call it only after every rank has
+ * passed a final cpb_peer_barrier (a peer may otherwise still be reading).  The mapped pointers of a
+ * destroyed segment dangle: drop every view of the segment first. */
 #define CPB_PEER_HANDLE_BYTES 64
 typedef struct cpb_peer cpb_peer;
 const char* cpb_peer_last_error(void);
@@ -274,6 +297,10 @@ int cpb_peer_barrier(cpb_peer* seg, void* stream);
 int cpb_peer_check(cpb_peer* seg, void* stream);
 int cpb_peer_allreduce_f64(cpb_peer* seg, size_t offset, size_t n, void* stream);
 int cpb_peer_bcast_f64(cpb_peer* seg, size_t offset, size_t n, int src, void* stream);
+int cpb_peer_allgather_f64(cpb_peer* seg, size_t offset, const size_t* counts /* world */, void* stream);
+int cpb_peer_redist_c2(cpb_peer* seg, size_t offset, long ld, int nstate, void* stream);
+int cpb_peer_allreduce_scalars(cpb_peer* seg, double* vals, int n, void* stream);
+int cpb_peer_set_timeout_ms(cpb_peer* seg, double ms);
 int cpb_peer_destroy(cpb_peer* seg);
 
 /* ---- meta-GGA (cntl%ttau): kinetic-energy density and its potential ---------------------------

@@ -26,7 +26,8 @@ MODULE cpb200_interfaces
   PUBLIC :: cpb_rhoofr, cpb_vpsi, cpb_rhoofr_lsd, cpb_vpsi_lsd, cpb_c0_invalidate
   PUBLIC :: cpb_rhoofr_kpt, cpb_vpsi_kpt, cpb_tauofr, cpb_vtaupsi, cpb_vofrho_local
   PUBLIC :: cpb_peer_create, cpb_peer_connect, cpb_peer_local_ptr, cpb_peer_allreduce_f64, &
-       cpb_peer_bcast_f64, cpb_peer_check, cpb_peer_destroy
+       cpb_peer_bcast_f64, cpb_peer_check, cpb_peer_destroy, cpb_peer_redist_c2, cpb_peer_allgather_f64, &
+       cpb_peer_allreduce_scalars, cpb_peer_set_timeout_ms
   PUBLIC :: cpb_error_message
 
   INTERFACE
@@ -196,6 +197,38 @@ MODULE cpb200_interfaces
        INTEGER(c_int), VALUE :: src
      END FUNCTION cpb_peer_bcast_f64
 
+     ! cp_grp_redist(C2_vpsi) of a device-resident run (vpsi_utils.mod.F90:708-712): all-gather of the
+     ! part_1d state blocks of the (ld, nstate) array that starts `offset` doubles into the segment
+     INTEGER(c_int) FUNCTION cpb_peer_redist_c2(seg, offset, ld, nstate, stream) BIND(c, name='cpb_peer_redist_c2')
+       IMPORT :: c_int, c_long, c_size_t, c_ptr
+       TYPE(c_ptr), VALUE :: seg, stream
+       INTEGER(c_size_t), VALUE :: offset
+       INTEGER(c_long), VALUE :: ld
+       INTEGER(c_int), VALUE :: nstate
+     END FUNCTION cpb_peer_redist_c2
+
+     INTEGER(c_int) FUNCTION cpb_peer_allgather_f64(seg, offset, counts, stream) BIND(c, name='cpb_peer_allgather_f64')
+       IMPORT :: c_int, c_size_t, c_ptr
+       TYPE(c_ptr), VALUE :: seg, stream
+       INTEGER(c_size_t), VALUE :: offset
+       INTEGER(c_size_t), INTENT(in) :: counts(*)        ! doubles per rank, even
+     END FUNCTION cpb_peer_allgather_f64
+
+     ! group-partial ekin / rsum_g / rsum_r summed over the groups (in rank order); synchronises
+     INTEGER(c_int) FUNCTION cpb_peer_allreduce_scalars(seg, vals, n, stream) BIND(c, name='cpb_peer_allreduce_scalars')
+       IMPORT :: c_int, c_double, c_ptr
+       TYPE(c_ptr), VALUE :: seg, stream
+       REAL(c_double), INTENT(inout) :: vals(*)
+       INTEGER(c_int), VALUE :: n
+     END FUNCTION cpb_peer_allreduce_scalars
+
+     INTEGER(c_int) FUNCTION cpb_peer_set_timeout_ms(seg, ms) BIND(c, name='cpb_peer_set_timeout_ms')
+       IMPORT :: c_int, c_double, c_ptr
+       TYPE(c_ptr), VALUE :: seg
+       REAL(c_double), VALUE :: ms
+     END FUNCTION cpb_peer_set_timeout_ms
+
+     ! mandatory after the collectives of a step: CPB_ERR_CUDA if a rank missed a barrier
      INTEGER(c_int) FUNCTION cpb_peer_check(seg, stream) BIND(c, name='cpb_peer_check')
        IMPORT :: c_int, c_ptr
        TYPE(c_ptr), VALUE :: seg, stream
