@@ -129,23 +129,45 @@ class ClockSampler:
         return out
 
 
+def _cpu_legs(n, states_seed, sample_states, probe_states=16):
+    """The two CPU restatements of the reference algorithm (both "port": the reference is Fortran + FFTW +
+    MPI and cannot be built in this image): oracle/staged_oracle.c (built-in mixed-radix FFT, in the style
+    of mltfft_default) and oracle/staged_pocketfft.py (the same staged passes with a library FFT - pocketfft
+    - in the role FFTW plays in the reference's FFTW build).  Both run on every core of the affinity mask
+    (NOT OMP_NUM_THREADS: torchrun exports 1).  Returns (geo, c0, f, v, cores, name, module) of the faster
+    one, decided on a short probe."""
+    from oracle import cpmd_oracle as orc
+    from oracle import staged, staged_pocketfft
+
+    cores = staged_pocketfft.set_threads(0)       # sets the OpenMP team of both and pocketfft's workers
+    geo = orc.make_geometry(n)
+    c0, f, v = orc.synthetic_inputs(geo, sample_states, seed=states_seed)
+    rates = {}
+    for name, mod in (("staged_oracle.c (built-in FFT)", staged), ("staged_pocketfft.py (library FFT)", staged_pocketfft)):
+        ns = min(probe_states, sample_states)
+        mod.rhoofr(geo, c0[:2], f[:2], 1.0, 1.0)           # page faults, thread pools
+        t0 = time.perf_counter()
+        mod.rhoofr(geo, c0[:ns], f[:ns], 1.0, 1.0)
+        mod.vpsi(geo, c0[:ns], np.zeros_like(c0[:ns]), f[:ns], v, 1.0)
+        rates[name] = 3.0 * ns / (time.perf_counter() - t0)
+    best = max(rates, key=rates.get)
+    mod = staged if best.startswith("staged_oracle") else staged_pocketfft
+    return geo, c0, f, v, cores, best, mod, rates
+
+
 def run_reference(args, rank, world):
-    """The reference arm: the CPU restatement of fftnew's staged algorithm on the host cores."""
+    """The reference arm: the CPU restatement of fftnew's staged algorithm on the host cores (the faster
+    of the two ports), every core of the box, a bounded sample of the workload per step."""
     if rank != 0:
         return
-    from oracle import cpmd_oracle as orc
-    from oracle import staged
-
-    cores = staged.set_threads(0)
     n = args.mesh
-    sample_states = args.ref_sample_states
-    geo = orc.make_geometry(n)
-    c0, f, v = orc.synthetic_inputs(geo, sample_states, seed=1234 + n + 7 * args.states)
+    sample_states = min(args.ref_sample_states, args.states)
+    geo, c0, f, v, cores, which, mod, rates = _cpu_legs(n, 1234 + n + 7 * args.states, sample_states)
     c2 = np.zeros_like(c0)
 
     def step():
-        staged.rhoofr(geo, c0, f, 1.0, 1.0)
-        staged.vpsi(geo, c0, c2, f, v, 1.0)
+        mod.rhoofr(geo, c0, f, 1.0, 1.0)
+        mod.vpsi(geo, c0, c2, f, v, 1.0)
 
     for _ in range(args.warmup):
         step()
@@ -154,15 +176,22 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = 3.0 * sample_states / dt
-    sample = f"{sample_states} of {args.states} states ({(sample_states + 1) // 2} packed pairs), mesh {n}^3, rhoofr+vpsi"
+    sample = (f"{sample_states} of {args.states} states ({(sample_states + 1) // 2} packed pairs) per step, mesh {n}^3, "
+              f"rhoofr+vpsi, {which}")
+    cfg = _config(args, n_gpus=args.gpus)
+    cfg["reference_sample"] = sample
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "device": "cpu", "kind": "port", "host_cores": cores,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(args, n_gpus=args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "probe_band_ffts_per_s": rates},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "CPU measurement (no GPU work): the reference's algorithm restated in C / NumPy+pocketfft, "
+                "not the upstream Fortran build; `value` is normalised to band-FFTs/s from the sample",
     }
     _emit(line)
 
@@ -181,23 +210,19 @@ def _config(args, n_gpus):
 
 
 def cpu_baseline(args):
-    """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
-    from oracle import cpmd_oracle as orc
-    from oracle import staged
-
-    cores = staged.set_threads(0)
+    """Bounded sample of the same workload on the host cores (rank 0, N=1 only): the faster of the two CPU
+    ports, all cores."""
     n = args.mesh
     ns = min(args.cpu_sample_states, args.states)
-    geo = orc.make_geometry(n)
-    c0, f, v = orc.synthetic_inputs(geo, ns, seed=1234 + n + 7 * args.states)
+    geo, c0, f, v, cores, which, mod, rates = _cpu_legs(n, 1234 + n + 7 * args.states, ns)
     c2 = np.zeros_like(c0)
-    staged.rhoofr(geo, c0[:2], f[:2], 1.0, 1.0)   # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
-    staged.rhoofr(geo, c0, f, 1.0, 1.0)
-    staged.vpsi(geo, c0, c2, f, v, 1.0)
+    mod.rhoofr(geo, c0, f, 1.0, 1.0)
+    mod.vpsi(geo, c0, c2, f, v, 1.0)
     dt = time.perf_counter() - t0
     return {"value": 3.0 * ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{ns} of {args.states} states, mesh {n}^3, rhoofr+vpsi once ({dt:.1f} s)"}
+            "sample": f"{ns} of {args.states} states, mesh {n}^3, rhoofr+vpsi once ({dt:.1f} s), {which}",
+            "probe_band_ffts_per_s": rates}
 
 
 def widened_rows(args, dev, plan, c0, f_block, v, timed):
@@ -266,6 +291,46 @@ def widened_rows(args, dev, plan, c0, f_block, v, timed):
     return out
 
 
+def sweep_configs(args, dev, timed, peak):
+    """The other BASELINE.json configurations (configs[0], [1], [2] and two points of the configs[4] sweep) on
+    one GPU, device-resident, untimed in `value`: ms per CP step and the whole-step HBM roofline fraction
+    (algorithmic bytes of SURVEY 8d / measured copy rate)."""
+    import torch
+
+    from cpmd_b200 import Plan, synthetic
+
+    out = []
+    for label, n, ns in (("configs[0] single H2O, 72^3 x 4 states", 72, 4),
+                         ("configs[1] 64-atom Si, 96^3 x 128 states", 96, 128),
+                         ("configs[2] 32 H2O, 120^3 x 128 states", 120, 128),
+                         ("configs[4] sweep 256^3 x 64 states", 256, 64),
+                         ("configs[4] sweep 320^3 x 32 states", 320, 32)):
+        d = synthetic.make_inputs(n, ns)
+        plan = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], device=dev.index or 0, max_batch=args.batch)
+        c0 = torch.from_numpy(d["c0"]).to(dev)
+        v = torch.from_numpy(d["vpot"]).to(dev)
+        rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+        c2 = torch.zeros_like(c0)
+        f = d["f"]
+        res = {}
+
+        def step():
+            res["s"] = plan.rhoofr_dev(c0, f, rho)
+            plan.vpsi_dev(c0, c2, f, v)
+
+        ms = timed(step, 5, 3)
+        ek, rg, rr = res["s"]
+        bm = _byte_model(plan.info, ns)
+        out.append({"workload": label, "mesh": n, "states": ns, "ms_per_step": ms,
+                    "band_ffts_per_s": 3.0 * ns / (ms * 1e-3),
+                    "step_algorithmic_GB": bm["step"] / 1e9,
+                    "step_frac": bm["step"] / (ms * 1e-3) / 1e9 / peak,
+                    "charge_identity_ok": bool(abs(rg - rr) < 1e-10 * max(rg, 1e-300))})
+        del plan, c0, c2, rho, v, d
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local):
     import torch
     import torch.distributed as dist
@@ -316,21 +381,78 @@ def run_ours(args, rank, world, local):
         rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
     _COLLECTIVES_USED["mode"] = collectives
     stream = torch.cuda.current_stream()
+    # the V broadcast runs on a side stream: only the first z pass of vpsi reads V (cpb_plan_set_vpot_event),
+    # so the gather and the x / y passes of the first batch overlap it.  In a CP step V derives from the
+    # group-summed rho, so the broadcast is ordered after the all-reduce.
+    side = torch.cuda.Stream(device=dev, priority=-1) if seg is not None else None
+    overlap_bcast = seg is not None and os.environ.get("CPB_BCAST_OVERLAP", "1") != "0"
 
-    def redist_and_bcast():
+    def step_device():
+        """rhoofr on the rank's block -> cp_grp_redist(rho) + the 3 group-partial scalars -> V broadcast ->
+        vpsi on the rank's block.  Returns the group-summed (ekin, rsum_g, rsum_r)."""
+        ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
         if seg is not None:
             seg.allreduce(0, nn, stream=stream)        # cp_grp_redist(rhoe), rhoofr_utils.mod.F90:457-461
-            seg.bcast(nn, nn, src=0, stream=stream)    # V(r) once per step
+            if overlap_bcast:
+                done = torch.cuda.Event()
+                done.record(stream)
+                side.wait_event(done)
+                seg.bcast(nn, nn, src=0, stream=side)  # V(r) once per step
+                vready = torch.cuda.Event()
+                vready.record(side)
+                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)   # SURVEY 8e: the 2-3 doubles
+                plan.set_vpot_event(vready)
+            else:
+                seg.bcast(nn, nn, src=0, stream=stream)
+                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)
         elif world > 1:
             cdist.cp_grp_redist(rho)
             cdist.bcast_potential(v, src=0)
-
-    def step_device():
-        # rhoofr on the rank's block (local indices: the block is a contiguous state range)
-        ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
-        redist_and_bcast()
+            ek, rg, rr = cdist.redist_scalars(ek, rg, rr, device=dev)
         plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
         return ek, rg, rr
+
+    def checks():
+        """Parity evidence on the timed configuration itself: the reference's charge self-check
+        (rhoofr_utils.mod.F90:607-635) on the group-summed density, the energy identity that links the two
+        routines (-sum dotp(c0,c2) = ekin + 1/N sum V rho) with group-summed scalars, and - N > 1 -
+        64-bit checksums of rho and V on every rank (the peer all-reduce promises bit-identical ranks)."""
+        c2.zero_()
+        ek, rg, rr = step_device()
+        torch.cuda.synchronize()
+        if seg is not None:
+            seg.check()
+        npts = float(n) ** 3
+        rr_reduced = rho.sum().item() * plan.omega / npts           # from the all-reduced array itself
+        w = torch.full((plan.ngw,), 2.0, dtype=torch.float64, device=dev)
+        w[0] = 1.0
+        occ = torch.from_numpy((f_block != 0).astype(np.float64)).to(dev)
+        dot = ((c0.real * c2.real + c0.imag * c2.imag) * w).sum(dim=1)
+        dot = (dot * occ).sum().item()
+        vrho = (v * rho).sum().item() / npts
+        sums = [int(rho.view(torch.int64).sum().item()), int(v.view(torch.int64).sum().item())]
+        if world > 1:
+            t = torch.tensor([dot], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            dot = t.item()
+            ck = torch.tensor(sums, dtype=torch.int64, device=dev)
+            allck = [torch.empty_like(ck) for _ in range(world)]
+            dist.all_gather(allck, ck)
+            identical = all(torch.equal(a, allck[0]) for a in allck)
+        else:
+            identical = None
+        e_test = ek + vrho
+        out = {
+            "charge_identity": {"rsum_g": rg, "rsum_r_of_reduced_rho": rr_reduced, "rsum_r_from_partials": rr,
+                                "ok": bool(abs(rr_reduced - rg) < 1e-10 * rg and abs(rr - rg) < 1e-10 * rg)},
+            "energy_identity": {"minus_sum_dotp_c0_c2": -dot, "ekin_plus_int_V_rho": e_test,
+                                "ok": bool(abs(-dot - e_test) < 1e-9 * max(1.0, abs(e_test)))},
+            "ranks_bit_identical": {"rho_and_V_checksums_equal": identical,
+                                    "ok": bool(identical) if world > 1 else True},
+        }
+        out["all_ok"] = all(v_["ok"] for v_ in out.values())
+        c2.zero_()
+        return out
 
     def barrier():
         if world > 1:
@@ -373,9 +495,14 @@ def run_ours(args, rank, world, local):
         if go:
             break
         step_device()
+    check_result = checks()
+    if not check_result["all_ok"]:
+        print(f"bench.py: PARITY CHECKS FAILED on the timed configuration: {json.dumps(check_result)}", file=sys.stderr)
     l0 = plan.launch_count
     ms_step = timed(step_device, args.steps, 0)
     launches = plan.launch_count - l0
+    if seg is not None:
+        seg.check()                    # mandatory: a barrier timeout inside the timed region voids the number
     clocks = sampler.stop() if sampler else None
     value = 3.0 * nstate / (ms_step * 1e-3)
 
@@ -384,7 +511,12 @@ def run_ours(args, rank, world, local):
     # recomputed.  Reported separately as ms per CP step; `value` above never uses it.
     def step_device_keep():
         plan.rhoofr_dev(c0, f_block, rho, stream=stream, flags=lib.CPB_PSI_KEEP)
-        redist_and_bcast()
+        if seg is not None:
+            seg.allreduce(0, nn, stream=stream)
+            seg.bcast(nn, nn, src=0, stream=stream)
+        elif world > 1:
+            cdist.cp_grp_redist(rho)
+            cdist.bcast_potential(v, src=0)
         plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_PSI_REUSE)
 
     ms_step_keep = timed(step_device_keep, max(1, min(args.steps, 3)), 1)
@@ -443,8 +575,10 @@ def run_ours(args, rank, world, local):
     e2e_value = 3.0 * nstate / (ms_e2e * 1e-3)
 
     extras = None
+    sweep = None
     if world == 1 and not args.no_extras:
         extras = widened_rows(args, dev, plan, c0, f_block, v, timed)
+        sweep = sweep_configs(args, dev, timed, _peaks()[0])
 
     if rank != 0:
         return
@@ -471,7 +605,7 @@ def run_ours(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(args, world),
-        "clocks": clocks,
+        "clocks": clocks, "checks": check_result,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "steps": e2e_steps,
                 "api": "cpb_rhoofr(CPB_C0_KEEP) + cpb_vpsi(CPB_C0_REUSE), pinned host buffers, c2 += semantics"},
@@ -499,6 +633,8 @@ def run_ours(args, rank, world, local):
     }
     if extras is not None:
         line["widened_rows"] = extras
+    if sweep is not None:
+        line["sweep"] = sweep
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     _emit(line)
@@ -535,7 +671,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sample-states", type=int, default=96,
                     help="states per step of the --impl reference arm (bounded sample of the workload)")
-    ap.add_argument("--cpu-sample-states", type=int, default=512,
+    ap.add_argument("--cpu-sample-states", type=int, default=256,
                     help="states of the cpu_baseline leg (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the widened-row measurements (vofrho, k-points, tau)")

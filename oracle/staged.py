@@ -34,7 +34,19 @@ def load():
     return _lib
 
 
+def host_cores():
+    """Cores this process may run on (sched affinity), NOT OMP_NUM_THREADS: torchrun exports
+    OMP_NUM_THREADS=1, which made the round-1 reference arm run on one core at N > 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def set_threads(n=0):
+    """n <= 0: one thread per core of the affinity mask."""
+    if n <= 0:
+        n = host_cores()
     return load().orc_set_threads(int(n))
 
 

@@ -649,3 +649,42 @@ def test_randomised_meshes_cutoffs_and_orders(emu_cdll):
         tag = f"case {case}: mesh {nr}, radius {rad:.2f}, ngw {geo.ngw}, {ns} states, {ngroups} groups, {p.info['band_pruned']}"
         assert relmax(acc, ref["rhoe"]) < RTOL, tag
         assert relmax(c2, orc.vpsi(geo, c0, 0.25 * c0, f, v, 0.9)[:, perm]) < RTOL, tag
+
+
+@pytest.mark.parametrize("nr,scale", [(24, 0.62), ((20, 24, 30), 0.6), (48, 0.62)])
+def test_general_cell_reciprocal_vectors(emu_cdll, nr, scale):
+    """Non-orthorhombic cell: the cutoff region is an oblique ellipsoid in index space
+    and hg is not an integer (loadpa_utils.mod.F90:286-335, rggen_utils.mod.F90:121-129)."""
+    if isinstance(nr, int):
+        nr = (nr, nr, nr)
+    b = np.array([[1.0, 0.0, 0.0], [0.27, 1.06, 0.0], [0.14, -0.21, 0.93]])
+    geo = orc.make_geometry(nr, gcutw=scale * (min(nr) / 4.0) ** 2, b=b)
+    assert np.abs(geo.hg - np.round(geo.hg)).max() > 1e-3
+    tpiba2, omega = 0.83, 41.7
+    c0, f, v = orc.synthetic_inputs(geo, 5, f_pattern="mixed")
+    p = Plan(nr, geo.inyh, geo.hg, tpiba2, omega, max_batch=2, _cdll=emu_cdll)
+    nz, iz = p.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)
+    rho, ekin, rg, rr = p.rhoofr(c0, f)
+    ref = orc.rhoofr(geo, c0, f, omega, tpiba2)
+    assert relmax(rho, ref["rhoe"]) < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"])) and abs(rg - ref["rsum_g"]) < ETOL
+    assert abs(rr - ref["rsum_r"]) < ETOL
+    c2 = 0.5 * c0
+    c2_ref = orc.vpsi(geo, c0, c2, f, v, tpiba2)
+    p.vpsi(c0, c2, f, v)
+    assert relmax(c2, c2_ref) < RTOL
+
+
+def test_charge_check_flag(emu_cdll):
+    """rhoofr_utils.mod.F90:625-635: |rsum_r - rsum_g| > 1e-6 stops the run (opt-in: CPB_RHO_CHECK_CHARGE)."""
+    d = synthetic.make_inputs(16, 4)
+    p = _plan(d, emu_cdll, max_batch=2)
+    p.rhoofr(d["c0"], d["f"], flags=lib.CPB_RHO_CHECK_CHARGE)
+    bad = d["c0"].copy()
+    bad[1, 0] = 0.4 + 0.3j                 # G = 0 coefficient not real: not a real function
+    with pytest.raises(CpbError) as ei:
+        p.rhoofr(bad, d["f"], flags=lib.CPB_RHO_CHECK_CHARGE)
+    assert ei.value.code == lib.CPB_ERR_CHARGE
+    _, _, rg, rr = p.rhoofr(bad, d["f"])
+    assert abs(rg - rr) > 1e-6

@@ -164,3 +164,26 @@ def test_peer_barrier_timeout_is_reported(tmp_path):
     mp.spawn(_late_worker, args=(2, 29613, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert "timeout" in open(tmp_path / f"msg_{r}.txt").read()
+
+
+def test_one_process_two_devices():
+    """plans on two devices in ONE process - the opt-in to > 48 KB of dynamic shared memory
+    is per device (the 192-point kernels need it)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one box")
+    from cpmd_b200 import Plan, synthetic
+
+    d = synthetic.make_inputs(192, 4)
+    out = []
+    for di in (0, 1):
+        dev = torch.device("cuda", di)
+        plan = Plan(d["nr"], d["inyh"], d["hg"], device=di, max_batch=2)
+        with torch.cuda.device(dev):
+            c0 = torch.from_numpy(d["c0"]).to(dev)
+            rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+            plan.rhoofr_dev(c0, d["f"], rho)
+            c2 = torch.zeros_like(c0)
+            plan.vpsi_dev(c0, c2, d["f"], torch.from_numpy(d["vpot"]).to(dev))
+            torch.cuda.synchronize(dev)
+        out.append((rho.cpu(), c2.cpu()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])

@@ -559,3 +559,105 @@ def test_low_dual_cutoff_unpruned_kernels_gpu(dev, n, ns):
     ref = orc.rhoofr(geo, c0, f, 1.3, 0.9)
     assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
     assert relmax(c2, orc.vpsi(geo, c0, 0.5 * c0, f, v, 0.9)) < RTOL
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the benchmarked launch shape, the remaining lengths, a general cell, error paths
+# ---------------------------------------------------------------------------------------------
+def test_production_shape_matches_staged_oracle(dev):
+    """The configuration bench.py times - 192^3, max_batch 32 (the plan's default x_sub, long per-block
+    pair loops, TMA rings reused many times) - on 132 states = 66 pairs in three batches (32 + 32 + 2),
+    mixed occupations, EVERY state of every batch element-wise against the threaded C restatement."""
+    n, ns = 192, 132
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=32)
+    assert plan.info["max_batch"] == 32
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    v = torch.from_numpy(d["vpot"]).to(dev)
+    rho = torch.full((plan.nnr1,), 7.0, dtype=torch.float64, device=dev)
+    ekin, rg, rr = plan.rhoofr_dev(c0, d["f"], rho)
+    c2 = 0.5 * c0
+    plan.vpsi_dev(c0, c2, d["f"], v)
+    torch.cuda.synchronize()
+    ref = staged.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rho.cpu().numpy(), ref["rhoe"]) < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
+    assert abs(rg - ref["rsum_g"]) < ETOL * rg and abs(rr - rg) < 1e-10 * rg
+    c2_ref = staged.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)
+    c2_h = c2.cpu().numpy()
+    for s in range(ns):                                # per state, so a wrong pair cannot hide in the norm
+        assert relmax(c2_h[s], c2_ref[s]) < RTOL, s
+    # the host-pointer entry points with the same launch shape, bit-identical
+    rho_h, ekin_h, rg_h, rr_h = plan.rhoofr(d["c0"], d["f"])
+    assert np.array_equal(rho_h, rho.cpu().numpy()) and (ekin_h, rg_h, rr_h) == (ekin, rg, rr)
+
+
+@pytest.mark.parametrize("n", [360, 384, 400])
+def test_largest_lengths_match_staged_oracle(dev, n):
+    """The three largest instantiated lengths (never run on a GPU)."""
+    d = synthetic.make_inputs(n, 2)
+    geo = orc.make_geometry(n)
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=1)
+    rho, (ekin, rg, rr), c2 = _dev_run(plan, d, dev)
+    ref = staged.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rho, ref["rhoe"]) < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"])) and abs(rr - rg) < ETOL
+    c2_ref = staged.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)
+    assert relmax(c2, c2_ref) < RTOL
+
+
+@pytest.mark.parametrize("nr,scale", [(48, 0.62), ((40, 48, 60), 0.55), (96, 0.6)])
+def test_general_cell_reciprocal_vectors(dev, nr, scale):
+    """Non-orthorhombic cell: b1,b2,b3 not the unit vectors, so the cutoff region is an oblique ellipsoid
+    in index space, hg is not an integer and the z band / ray table are not those of a sphere
+    (loadpa_utils.mod.F90:286-335 with the general |i b1 + j b2 + k b3|^2, rggen_utils.mod.F90:121-129)."""
+    if isinstance(nr, int):
+        nr = (nr, nr, nr)
+    b = np.array([[1.0, 0.0, 0.0], [0.27, 1.06, 0.0], [0.14, -0.21, 0.93]])
+    geo = orc.make_geometry(nr, gcutw=scale * (min(nr) / 4.0) ** 2, b=b)
+    assert np.abs(geo.hg - np.round(geo.hg)).max() > 1e-3
+    tpiba2, omega = 0.83, 41.7
+    c0, f, v = orc.synthetic_inputs(geo, 5, f_pattern="mixed")
+    plan = Plan(nr, geo.inyh, geo.hg, tpiba2, omega, max_batch=2)
+    nz, iz = plan.maps()
+    assert np.array_equal(nz, geo.nzhs) and np.array_equal(iz, geo.indzs)
+    d = dict(c0=c0, f=f, vpot=v)
+    rho, (ekin, rg, rr), c2 = _dev_run(plan, d, dev)
+    ref = orc.rhoofr(geo, c0, f, omega, tpiba2)
+    assert relmax(rho, ref["rhoe"]) < RTOL
+    assert abs(ekin - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
+    assert abs(rg - ref["rsum_g"]) < ETOL and abs(rr - ref["rsum_r"]) < ETOL
+    assert relmax(c2, orc.vpsi(geo, c0, 0.5 * c0, f, v, tpiba2)) < RTOL
+
+
+def test_c0_upload_and_charge_check(dev):
+    """cpb_c0_upload + CPB_C0_REUSE (the cp_cuwfn cache, vpsi_utils.mod.F90:268-273) and the reference's
+    charge self-check (rhoofr_utils.mod.F90:625-635) as CPB_ERR_CHARGE."""
+    from cpmd_b200.api import CpbError
+    n, ns = 48, 6
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    geo = orc.make_geometry(n)
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
+    plan.c0_upload(d["c0"])
+    poisoned = d["c0"].copy()
+    rho, ekin, rg, rr = plan.rhoofr(d["c0"], d["f"], flags=lib.CPB_C0_REUSE | lib.CPB_RHO_CHECK_CHARGE)
+    ref = orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(rg - rr) < 1e-9
+    # the kept block is what is used: the host array may change without effect while the key matches
+    keep = d["c0"].copy()
+    d["c0"][:] = 0.0
+    rho2, *_ = plan.rhoofr(d["c0"], d["f"], flags=lib.CPB_C0_REUSE)
+    assert np.array_equal(rho2, rho)
+    plan.c0_invalidate()
+    d["c0"][:] = keep
+    rho3, *_ = plan.rhoofr(d["c0"], d["f"], flags=lib.CPB_C0_REUSE)
+    assert np.array_equal(rho3, rho)
+    # a state whose G = 0 coefficient is not real is not a real function: the real-space charge and
+    # dotp (which counts Re^2 only at G = 0, dotp_utils.mod.F90:26-53) disagree -> the reference stops
+    poisoned[1, 0] = 0.4 + 0.3j
+    with pytest.raises(CpbError) as ei:
+        plan.rhoofr(poisoned, d["f"], flags=lib.CPB_RHO_CHECK_CHARGE)
+    assert ei.value.code == lib.CPB_ERR_CHARGE and "DENSITY SUMS" in str(ei.value)
+    _, _, rg_p, rr_p = plan.rhoofr(poisoned, d["f"])           # without the flag: sums returned, no error
+    assert abs(rg_p - rr_p) > 1e-6

@@ -422,3 +422,21 @@ def test_tau_known_answers():
         assert np.abs(t2.sum(axis=0) - tau).max() < 1e-14
         d2 = orc.vtaupsi(geo, c0, np.zeros_like(c0), f, gk, np.stack([v, v]), tp, nsup)
         assert np.abs(d2 - d).max() < 1e-15
+
+
+@pytest.mark.parametrize("nr,ns", [(16, 5), ((16, 20, 24), 4), (30, 7)])
+def test_pocketfft_staged_restatement_matches_dense(nr, ns):
+    """oracle/staged_pocketfft.py (the stronger CPU baseline of bench.py: fftnew's staged sparse passes with
+    a library 1-D FFT) against the dense NumPy restatement, all groupings."""
+    from oracle import staged_pocketfft as spf
+    geo = orc.make_geometry(nr)
+    c0, f, v = orc.synthetic_inputs(geo, ns, f_pattern="mixed")
+    for g, ng in ((0, 1), (0, 2), (2, 3)):
+        a = orc.rhoofr(geo, c0, f, 1.3, 0.9, g, ng)
+        b = spf.rhoofr(geo, c0, f, 1.3, 0.9, g, ng, batch=2)
+        assert np.abs(a["rhoe"] - b["rhoe"]).max() <= 1e-13 * max(np.abs(a["rhoe"]).max(), 1e-300)
+        for k in ("ekin", "rsum_g", "rsum_r"):
+            assert abs(a[k] - b[k]) < 1e-11
+        c2a = orc.vpsi(geo, c0, 0.5 * c0, f, v, 0.9, g, ng)
+        c2b = spf.vpsi(geo, c0, 0.5 * c0, f, v, 0.9, g, ng, batch=3)
+        assert np.abs(c2a - c2b).max() <= 1e-13 * np.abs(c2a).max()
