@@ -25,6 +25,13 @@ struct AxisKernels {
   void (*x_inv_gk)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
                    int ppg, bool half, const double* gk);
   void (*x_fwd)(cudaStream_t, const cplx* T1, cplx* G, const PlanDev&, int npair, int ppg, bool half);
+  // mirror-pair x passes of the Gamma-point hot path (kernels.h): a block owns rays and their mirrors.
+  // x_inv_m: kin_part != nullptr also accumulates the kin_energy / dotp partials, [pair][block][4];
+  // x_fwd_m: forward x pass fused with the unpack + kinetic + c2 update (acc: c2 += result)
+  void (*x_inv_m)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
+                  int ppg, bool half, double* kin_part, int geq0);
+  void (*x_fwd_m)(cudaStream_t, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev&, const PairDev&,
+                  int npair, int ppg, bool half, bool acc);
   // y/z passes work on one chunk of x tiles [xt0, xt0+nxc) (T2 holds that chunk only); `half`
   // selects the band-pruned instantiation (KRange), `ppg` = pairs per block (pair groups in grid.z)
   void (*y_inv)(cudaStream_t, const cplx* T1, cplx* T2, const PlanDev&, int npair, int xt0, int nxc,
@@ -42,6 +49,7 @@ struct AxisKernels {
                      bool acc, bool half);
   int yz_blocks_per_sm;  // occupancy the y/z kernels are compiled for
   int x_inv_blocks, x_fwd_blocks;  // same for the x kernels
+  int x_inv_m_blocks, x_fwd_m_blocks;
 };
 
 const AxisKernels* find_axis_kernels(int n);

@@ -87,6 +87,51 @@ void x_fwd(cudaStream_t st, const cplx* T1, cplx* G, const PlanDev& pd, int npai
   else x_fwd_t<false>(st, T1, G, pd, npair, ppg);
 }
 
+// blocks of the mirror-pair x kernels: H = SL/2 rays (+ their mirrors) each
+int x_m_blocks(const PlanDev& pd) { return ((pd.nrays + 1) / 2 + SL / 2 - 1) / (SL / 2); }
+
+template <bool HALF, bool KIN>
+void x_inv_m_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+               int ppg, double* kin_part, int geq0) {
+  using C = XCfg<R1, R2, SL>;
+  using M = XMCfg<R1, R2, SL, HALF>;
+  auto k = k_x_inv_m<R1, R2, SL, B, HALF, KIN>;
+  allow_smem(k, M::SMEM_INV);
+  CPB_LAUNCH(k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_INV, st, c0, ldc, T1, pd, pr,
+             npair, ppg, kin_part, geq0);
+}
+void x_inv_m(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+             int ppg, bool half, double* kin_part, int geq0) {
+  if (half) {
+    if (kin_part) x_inv_m_t<true, true>(st, c0, ldc, T1, pd, pr, npair, ppg, kin_part, geq0);
+    else x_inv_m_t<true, false>(st, c0, ldc, T1, pd, pr, npair, ppg, kin_part, geq0);
+  } else {
+    if (kin_part) x_inv_m_t<false, true>(st, c0, ldc, T1, pd, pr, npair, ppg, kin_part, geq0);
+    else x_inv_m_t<false, false>(st, c0, ldc, T1, pd, pr, npair, ppg, kin_part, geq0);
+  }
+}
+
+template <bool HALF, bool ACC>
+void x_fwd_m_t(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev& pd,
+               const PairDev& pr, int npair, int ppg) {
+  using C = XCfg<R1, R2, SL>;
+  using M = XMCfg<R1, R2, SL, HALF>;
+  auto k = k_x_fwd_m<R1, R2, SL, B, HALF, ACC>;
+  allow_smem(k, M::SMEM_FWD);
+  CPB_LAUNCH(k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_FWD, st, T1, c0, c2, ldc, pd, pr,
+             npair, ppg);
+}
+void x_fwd_m(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev& pd, const PairDev& pr,
+             int npair, int ppg, bool half, bool acc) {
+  if (half) {
+    if (acc) x_fwd_m_t<true, true>(st, T1, c0, c2, ldc, pd, pr, npair, ppg);
+    else x_fwd_m_t<true, false>(st, T1, c0, c2, ldc, pd, pr, npair, ppg);
+  } else {
+    if (acc) x_fwd_m_t<false, true>(st, T1, c0, c2, ldc, pd, pr, npair, ppg);
+    else x_fwd_m_t<false, false>(st, T1, c0, c2, ldc, pd, pr, npair, ppg);
+  }
+}
+
 constexpr size_t kSmemYZ2 = 2 * kSmemYZ;  // double-buffered exchange
 
 template <bool HALF>
@@ -171,8 +216,9 @@ void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const
 }
 
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
-                            x_inv, x_inv_gk, x_fwd, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real, YZBlocks<R1, R2>::v,
-                            XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD};
+                            x_inv, x_inv_gk, x_fwd, x_inv_m, x_fwd_m, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real,
+                            YZBlocks<R1, R2>::v, XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD,
+                            XMCfg<R1, R2, SL, true>::MINB_INV, XMCfg<R1, R2, SL, true>::MINB_FWD};
 
 }  // namespace
 

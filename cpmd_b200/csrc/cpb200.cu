@@ -111,6 +111,11 @@ struct cpb_plan {
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
+  bool mirror = false;        // mirror-pair x kernels usable (ray numbering mirror-symmetric; CPB_X_MIRROR=0 disables)
+  int nbx_m = 0;              // their blocks per pair group
+  double* d_kinpart = nullptr;  // kin_energy / dotp block partials of k_x_inv_m, [pair][nbx_m][4]
+  size_t kinpart_cap = 0;       // pairs
+  double* kin_cur = nullptr;    // set for the duration of a rhoofr call: partials of the call's pair 0
   const AxisKernels *kx = nullptr, *ky = nullptr, *kz = nullptr;
   // geometry (host copies)
   int xlo = 0, xhi = -1, zlo = 0, nzb = 0, nrays = 0, ref_nrays = 0, nrp = 0;
@@ -214,6 +219,7 @@ void free_plan(cpb_plan* p) {
   rt::dfree(p->d_cb);
   rt::hfree_pinned(p->h_pairs);
   rt::dfree(p->d_red);
+  rt::dfree(p->d_kinpart);
   rt::hfree_pinned(p->h_red);
   rt::dfree(p->d_c0);
   rt::dfree(p->d_c2);
@@ -391,12 +397,45 @@ int ew_ppg(const cpb_plan* p, int npair, int waves) {
   return (npair + groups - 1) / groups;
 }
 
-// x pass, inverse: one launch per batch; the kernel gathers the coefficients from c0 itself
-void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb) {
+// x pass, inverse: one launch per batch; the kernel gathers the coefficients from c0 itself.  Gamma point:
+// the mirror-pair kernel (each coefficient fetched once; with p->kin_cur set it also accumulates the
+// kin_energy / dotp partials of the batch's pairs, `off` = index of the batch's first pair in the call)
+void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb, int off = 0) {
   cudaStream_t st = w.s;
   Timed t(p, st, CPB_K_X_INV);
+  if (p->mirror && !p->kpt_mode) {
+    double* kin = p->kin_cur ? p->kin_cur + (size_t)off * p->nbx_m * 4 : nullptr;
+    p->kx->x_inv_m(st, c0, ldc, w.T1, p->pd, prb, nb, pairs_per_group(p, nb, p->nbx_m, p->kx->x_inv_m_blocks),
+                   p->half_x, kin, p->geq0);
+    return;
+  }
   p->kx->x_inv(st, c0, ldc, w.T1, p->kpt_mode ? p->pdk : p->pd, prb, nb,
                pairs_per_group(p, nb, p->nrp / p->kx->sl, p->kx->x_inv_blocks), p->half_x);
+}
+
+// room for the kin_energy / dotp block partials of `npairs` pairs; arms run_x_inv to produce them
+void kin_begin(cpb_plan* p, int npairs, int nblk, cudaStream_t st) {
+  p->kin_cur = nullptr;
+  if (!p->mirror || p->kpt_mode || npairs <= 0) return;
+  if ((size_t)npairs > p->kinpart_cap) {
+    rt::dfree(p->d_kinpart);
+    p->d_kinpart = nullptr;
+    p->kinpart_cap = 0;
+    p->d_kinpart = (double*)rt::dmalloc((size_t)npairs * p->nbx_m * 4 * sizeof(double));
+    p->kinpart_cap = (size_t)npairs;
+  }
+  rt::dzero(p->d_red, (size_t)kRedPerState * nblk * sizeof(double), st);
+  p->kin_cur = p->d_kinpart;
+}
+// fold the partials into d_red (k_kin_energy's layout, chunk 0); false if the separate pass is needed
+bool kin_end(cpb_plan* p, const PairDev& pr, int npairs, int first, cudaStream_t st) {
+  if (!p->kin_cur) return false;
+  p->kin_cur = nullptr;
+  auto k = k_kin_reduce;
+  Timed t(p, st, CPB_K_KIN);
+  CPB_LAUNCH(k, dim3(npairs), dim3(128), 4 * 128 * sizeof(double), st, (const double*)p->d_kinpart, p->nbx_m, pr, first,
+             p->d_red);
+  return true;
 }
 
 // x pass, forward, in sub-batches of x_sub pairs: k_x_fwd writes the sub-batch's band-ray storage
@@ -405,6 +444,13 @@ void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, co
 void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb,
                bool accumulate) {
   cudaStream_t st = w.s;
+  if (p->mirror && !p->kpt_mode) {
+    // Gamma point: forward x pass fused with the unpack (no band-ray storage, one launch per batch)
+    Timed t(p, st, CPB_K_X_FWD);
+    p->kx->x_fwd_m(st, w.T1, c0, c2, ldc, p->pd, prb, nb, pairs_per_group(p, nb, p->nbx_m, p->kx->x_fwd_m_blocks),
+                   p->half_x, accumulate);
+    return;
+  }
   for (int o = 0; o < nb; o += p->x_sub) {
     const int ns = std::min(p->x_sub, nb - o);
     PairDev prs = offset_pairs(prb, o);
@@ -521,7 +567,7 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
     cpb_plan::WorkSpace& w = p->ws[b % p->nws];
     if (hooks) hooks->before_batch(b, off, nb, w.s);
     PairDev prb = offset_pairs(pr, off);
-    run_x_inv(p, w, c0, ldc, prb, nb);
+    run_x_inv(p, w, c0, ldc, prb, nb, off);
     for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
       const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
       cplx* T2 = keep ? keep + (size_t)off * p->t2_pair : w.T2;
@@ -836,6 +882,22 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
         if (std::atoi(e)) p->half_x = p->half_y = p->half_z = false;
       }
     }
+    {
+      // mirror-pair x kernels: the mirror of internal ray r must be ray nrays - 1 - r (true whenever the ray
+      // set is symmetric under (y,z) -> (n2-y, n3-z), which the -G marks above guarantee) and the centre of
+      // the x axis must lie in the decimated index R1/2 of the kernels' factorisation (n1 even)
+      bool ok = (n1 % 2 == 0);
+      for (int zr = 0; zr < nzb && ok; ++zr)
+        for (int y = ylo[zr]; y <= yhi[zr] && ok; ++y) {
+          const int r = rayoff[zr] + (y - ylo[zr]);
+          ok = ray_of(n2 - y, n3 - (zlo + zr)) == nrays - 1 - r;
+        }
+      p->mirror = ok;
+      if (const char* e = std::getenv("CPB_X_MIRROR")) {
+        if (!std::atoi(e)) p->mirror = false;
+      }
+      p->nbx_m = ((nrays + 1) / 2 + SL / 2 - 1) / (SL / 2);
+    }
     p->xlo = xlo;
     p->xhi = xhi;
     p->zlo = zlo;
@@ -1048,9 +1110,11 @@ static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nsta
     rho_coefs(p, all, f, keep, pairs, ca, cb);
     ensure_red(p, kRedPerState * nblk + 3 * kSumBlocks);
     rt::dzero(rhoe_dev, (lsd ? 2 : 1) * nnr1 * sizeof(double), st);  // rhoofr_utils.mod.F90:198
-    launch_kin(p, c0, ld_c0, first, nblk, st);                        // :178
-    run_rhoofr(p, c0, ld_c0, upload_pairs(p, pairs, ca, cb, st), (int)pairs.size(), count_chan0(pairs), rhoe_dev,
-               rhoe_dev + nnr1, keep ? p->T2keep : nullptr, st, nullptr);
+    const PairDev prd = upload_pairs(p, pairs, ca, cb, st);
+    kin_begin(p, (int)pairs.size(), nblk, st);                        // :178 kin_energy rides on the gather ...
+    run_rhoofr(p, c0, ld_c0, prd, (int)pairs.size(), count_chan0(pairs), rhoe_dev, rhoe_dev + nnr1,
+               keep ? p->T2keep : nullptr, st, nullptr);
+    if (!kin_end(p, prd, (int)pairs.size(), first, st)) launch_kin(p, c0, ld_c0, first, nblk, st);  // ... or runs alone
     if (keep) psi_key_set(p, c0_dev, ld_c0, nstate, ngroups, my_group, nsup, (int)pairs.size());
     double* d_sums = p->d_red + kRedPerState * nblk;
     if (lsd) launch_lsd_sums(p, rhoe_dev, rhoe_dev + nnr1, nnr1, d_sums, ngroups == 1, st);  // :543-559

@@ -386,6 +386,365 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mirror-pair x passes (the Gamma-point hot path of rhoofr / vpsi).
+//
+// A plane wave G sits at (x, ray) and its partner -G at (n1 - x, mirror ray): the ray of (n2 - y, n3 - z).
+// The internal ray numbering (z-major, dense in y) makes the mirror of ray r simply nrays - 1 - r (the
+// plan verifies it).  A block owns H = SL/2 rays AND their mirrors (slots 0..H-1: rays H*bx + s, slots
+// H..SL-1: their mirrors), so both halves of every +-G couple live in the same block:
+//   k_x_inv_m   each coefficient c(ig) is fetched ONCE (by the thread that owns the +G position, x >=
+//               n1/2) and the thread that owns the -G position reads it from the owner's shared-memory
+//               stage: half the divergent 16-byte gathers of k_x_inv.  KIN: the owner also accumulates
+//               hg |c|^2 and dotp's w |c|^2 (kin_energy_utils.mod.F90:62-110, dotp_utils.mod.F90:26-53),
+//               so rhoofr needs no separate pass over c0.
+//   k_x_fwd_m   after the forward x pass the block holds FFT[V psi] at +G and at -G: the +-G
+//               separation, the kinetic term, the -f/2 scale and the c2 update (vpsi_utils.mod.F90:
+//               626-673, add_wfn :717) happen right there - no band-ray storage in HBM, no k_unpack.
+// Position classes along a ray (x = rA + R2 k): k < R1/2 lies below the centre plane (only -G partners or
+// nothing), k > R1/2 above it (only +G or nothing), k == R1/2 contains the centre plane x = n1/2 (either).
+// The staged / exchanged slots are indexed by k - R1/2 of the +G position, NPOS = KR::hi - R1/2 per thread.
+// The centre ray (odd nrays) is its own mirror: its mirror slot is switched off and its -G positions
+// read the ray's own slots.
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2, int SL, bool HALF>
+struct XMCfg {
+  using C = XCfg<R1, R2, SL>;
+  using KR = KRange<R1, HALF>;
+  static constexpr int H = SL / 2;
+  static constexpr int C0 = R1 / 2;              // first decimated index that can hold a +G position
+  static constexpr int NPOS = KR::hi - C0;
+  static constexpr int NA = C::NA;
+  static constexpr int NW = (C::NT + 31) / 32;
+  // inverse: exchange + twiddles + 2 gather stages [state][NPOS][NA] (+ reduction scratch with KIN)
+  static constexpr size_t SMEM_INV = (size_t)(C::SX_ELEMS + C::N + 2 * 2 * NPOS * NA) * sizeof(cplx) +
+                                     (size_t)(4 * NA + 2 * 4 * 8) * sizeof(double);
+  // forward: exchange + partner exchange [NPOS][NA] + staged c0 / c2 values [4][NPOS][NA]
+  static constexpr size_t SMEM_FWD = (size_t)(C::SX_ELEMS + NPOS * NA + 4 * NPOS * NA) * sizeof(cplx);
+  static constexpr int MINB_INV = (C::NT <= 128) ? ((C::RM <= 16) ? 4 : 3) : 2;
+  static constexpr int MINB_FWD = (C::NT <= 128) ? 3 : 2;
+};
+
+// ray of slot s of block bx; valid = false: the slot does nothing.  self = true: the ray is its own mirror
+// (the slot reads its own stage for the -G positions); otherwise the partner is slot (s + H) % SL.
+struct XSlot {
+  int ray;
+  bool valid, self;
+};
+template <int SL>
+CPB_D XSlot x_slot(int bx, int s, int nrays) {
+  constexpr int H = SL / 2;
+  const int base = bx * H + (s % H);
+  const int nhalf = (nrays + 1) / 2;
+  XSlot o;
+  o.self = (2 * base == nrays - 1);
+  o.valid = base < nhalf && !(s >= H && o.self);
+  o.ray = (s < H) ? base : nrays - 1 - base;
+  return o;
+}
+
+template <int R1, int R2, int SL, int B, bool HALF, bool KIN>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::MINB_INV))
+    k_x_inv_m(const cplx* CPB_RESTRICT c0, long ldc, cplx* CPB_RESTRICT T1, PlanDev pd, PairDev pr, int npair,
+              int ppg, double* CPB_RESTRICT kin_part, int geq0) {
+  using C = XCfg<R1, R2, SL>;
+  using M = XMCfg<R1, R2, SL, HALF>;
+  using KR = KRange<R1, HALF>;
+  constexpr int N = C::N, NT = C::NT, P1 = C::P1, NA = C::NA, H = M::H, C0 = M::C0, NPOS = M::NPOS;
+  CPB_DYN_SMEM(cplx, S);
+  cplx* SX = S;
+  cplx* TW = S + C::SX_ELEMS;
+  cplx* ST = TW + N;                                     // [buf][state][NPOS][NA]
+  double* RED = reinterpret_cast<double*>(ST + 2 * 2 * NPOS * NA);   // [4][NA]
+  double* RED2 = RED + 4 * NA;                           // [2][4][8], alternating per pair
+  const int tid = threadIdx.x;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+#if CPB_X_ROT
+  const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;  // see k_x_inv
+#else
+  const int tidA = tid;
+#endif
+  const int slotA = tidA % SL, rA = tidA / SL;           // slot-major role
+  const int pB = tid % R1, slotB = tid / R1;             // x-major role (valid if slotB < SL)
+  const XSlot sa = x_slot<SL>(blockIdx.x, slotA, pd.nrays);
+  const XSlot sb = x_slot<SL>(blockIdx.x, slotB < SL ? slotB : 0, pd.nrays);
+  const bool actA = rA < R2;
+  const bool okB = slotB < SL && sb.valid;
+  const int spA = sa.self ? slotA : (slotA + H) % SL;    // slot that stages my -G partners
+  const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
+  for (int i = tid; i < N; i += NT) TW[i] = pd.tw1[i];
+  // my band positions -> plane-wave index (bit 31: -G partner) or kNoPW
+  uint32_t tab[KR::cnt];
+  double hgv[NPOS];
+  static_for<0, KR::cnt>([&](auto kk) {
+    constexpr int j = decltype(kk)::value;
+    constexpr int k = KR::lo + j;
+    const int xb = rA + R2 * k - pd.xlo;
+    tab[j] = (actA && sa.valid && xb >= 0 && xb < pd.nxb) ? __ldg(&pd.gtab[(size_t)xb * pd.nrp + sa.ray]) : kNoPW;
+    if constexpr (k < C0) {
+      if (!(tab[j] & kNegPW)) tab[j] = kNoPW;            // below the centre plane only -G partners exist
+    }
+    if constexpr (KIN && k >= C0) {
+      hgv[k - C0] = (tab[j] != kNoPW && !(tab[j] & kNegPW)) ? __ldg(&pd.hg[tab[j]]) : 0.0;
+    }
+  });
+  auto gather = [&](int pair, int buf) {
+    const int s1 = __ldg(&pr.st1[pair]), s2 = __ldg(&pr.st2[pair]);
+    const cplx* c1p = c0 + (size_t)s1 * ldc;
+    const cplx* c2p = c0 + (size_t)(s2 < 0 ? s1 : s2) * ldc;
+    cplx* st = ST + (size_t)buf * (2 * NPOS * NA);
+    static_for<C0, KR::hi>([&](auto kk) {
+      constexpr int k = decltype(kk)::value;
+      constexpr int j = k - KR::lo;
+      if (tab[j] != kNoPW && !(tab[j] & kNegPW)) {
+        cp_async16(&st[(0 * NPOS + (k - C0)) * NA + tidA], c1p + tab[j]);
+        if (s2 >= 0) cp_async16(&st[(1 * NPOS + (k - C0)) * NA + tidA], c2p + tab[j]);
+      }
+    });
+    cp_async_commit();
+  };
+  if (actA && p0 < p1) gather(p0, 0);
+  for (int pair = p0; pair < p1; ++pair) {
+    const int buf = (pair - p0) & 1;
+    if (actA) cp_async_wait_all();
+    __syncthreads();  // the stage of this pair is complete and visible to the partner threads; SX and TW are free / ready
+    if (actA) {
+      if (pair + 1 < p1) gather(pair + 1, buf ^ 1);      // the other stage was last read one iteration ago
+      const bool two = __ldg(&pr.st2[pair]) >= 0;
+      const cplx* st = ST + (size_t)buf * (2 * NPOS * NA);
+      double sk1 = 0.0, sd1 = 0.0, sk2 = 0.0, sd2 = 0.0;
+      cplx v[R1];
+      static_for<0, R1>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        if constexpr (k >= KR::lo && k < KR::hi) {
+          constexpr int j = k - KR::lo;
+          const uint32_t e = tab[j];
+          v[k] = mk(0.0, 0.0);
+          if (e != kNoPW) {
+            if (k >= C0 && !(e & kNegPW)) {
+              // +G: c1 + i c2
+              const cplx a = st[(0 * NPOS + (k - C0)) * NA + tidA];
+              const cplx bq = two ? st[(1 * NPOS + (k - C0)) * NA + tidA] : mk(0.0, 0.0);
+              v[k] = mk(a.x - bq.y, a.y + bq.x);
+              if constexpr (KIN && k >= C0) {
+                const double m1 = a.x * a.x + a.y * a.y, m2 = bq.x * bq.x + bq.y * bq.y;
+                const bool g0 = (e == 0u) && geq0;       // dotp counts the real part of G = 0 once
+                sk1 += hgv[k - C0] * m1;
+                sk2 += hgv[k - C0] * m2;
+                sd1 += g0 ? a.x * a.x : 2.0 * m1;
+                sd2 += g0 ? bq.x * bq.x : 2.0 * m2;
+              }
+            } else {
+              // -G: conj(c1) + i conj(c2) of the coefficient staged by the owner of (n1 - x, mirror ray)
+              const int xm = pd.n1 - (rA + R2 * k);
+              const int idx = (xm / R2 - C0) * NA + (xm % R2) * SL + spA;
+              const cplx a = st[0 * NPOS * NA + idx];
+              const cplx bq = two ? st[1 * NPOS * NA + idx] : mk(0.0, 0.0);
+              v[k] = mk(a.x + bq.y, bq.x - a.y);
+            }
+          }
+        } else {
+          v[k] = mk(0.0, 0.0);
+        }
+      });
+      if constexpr (KIN) {
+        RED[0 * NA + tidA] = sk1;
+        RED[1 * NA + tidA] = sd1;
+        RED[2 * NA + tidA] = sk2;
+        RED[3 * NA + tidA] = sd2;
+      }
+      cplx* dst = SX + (rA * SL + slotA) * P1;
+      pass_a_st<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, [&](int p, cplx o) { dst[p] = o; });
+    }
+    __syncthreads();
+    if constexpr (KIN) {
+      // fixed-order reduction of the NA per-thread partials in three steps (NA -> 8 -> 1 per quantity); the
+      // last step of a pair runs one iteration later, so no barrier is added
+      if (pair > p0 && tid < 4) {
+        const double* r2 = RED2 + ((pair - 1 - p0) & 1) * 32;
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += r2[tid * 8 + i];
+        kin_part[((size_t)(pair - 1) * gridDim.x + blockIdx.x) * 4 + tid] = s;
+      }
+    }
+    if (slotB < SL) {
+      cplx u[R2];
+      static_for<0, R2>([&](auto aa) {
+        constexpr int a = decltype(aa)::value;
+        u[a] = SX[(a * SL + slotB) * P1 + pB];
+      });
+      dft<R2, true>(u);
+      if (okB) {
+        cplx* dst = T1 + (size_t)pair * t1_pair + (size_t)sb.ray * B;
+        static_for<0, R2>([&](auto qq) {
+          constexpr int q = decltype(qq)::value;
+          const int x = pB + R1 * q;
+          st_stream(&dst[(size_t)(x / B) * pd.nrays * B + (x % B)], u[q]);
+        });
+      }
+    }
+    if constexpr (KIN) {
+      if (tid < 32) {
+        const int q = tid / 8, part = tid % 8;
+        constexpr int PER = (NA + 7) / 8;
+        double s = 0.0;
+        for (int i = part * PER; i < (part + 1) * PER && i < NA; ++i) s += RED[q * NA + i];
+        RED2[((pair - p0) & 1) * 32 + q * 8 + part] = s;
+      }
+    }
+  }
+  if constexpr (KIN) {
+    __syncthreads();
+    if (p1 > p0 && tid < 4) {
+      const double* r2 = RED2 + ((p1 - 1 - p0) & 1) * 32;
+      double s = 0.0;
+      for (int i = 0; i < 8; ++i) s += r2[tid * 8 + i];
+      kin_part[((size_t)(p1 - 1) * gridDim.x + blockIdx.x) * 4 + tid] = s;
+    }
+  }
+}
+
+// forward x pass fused with the unpack of vpsi (see the header comment above).  pr.ca / pr.cb = fi / fip1
+// (vpsi_utils.mod.F90:627-633).  ACC: c2 += result (reference semantics), else c2 = result.
+template <int R1, int R2, int SL, int B, bool HALF, bool ACC>
+CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::MINB_FWD))
+    k_x_fwd_m(const cplx* CPB_RESTRICT T1, const cplx* CPB_RESTRICT c0, cplx* c2, long ldc, PlanDev pd, PairDev pr,
+              int npair, int ppg) {
+  using C = XCfg<R1, R2, SL>;
+  using M = XMCfg<R1, R2, SL, HALF>;
+  using KR = KRange<R1, HALF>;
+  constexpr int NT = C::NT, P1 = C::P1, NA = C::NA, H = M::H, C0 = M::C0, NPOS = M::NPOS;
+  CPB_DYN_SMEM(cplx, S);
+  cplx* SX = S;
+  cplx* EX = S + C::SX_ELEMS;         // [NPOS][NA]: FFT[V psi] at the -G partner of my +G positions
+  cplx* CS = EX + NPOS * NA;          // [4][NPOS][NA]: c0(ig, s1), c0(ig, s2), c2(ig, s1), c2(ig, s2)
+  const int tid = threadIdx.x;
+  const int p0 = blockIdx.y * ppg;
+  const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+#if CPB_X_ROT
+  const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;  // see k_x_inv
+#else
+  const int tidA = tid;
+#endif
+  const int slotA = tidA % SL, rA = tidA / SL;
+  const int pB = tid % R1, slotB = tid / R1;
+  const XSlot sa = x_slot<SL>(blockIdx.x, slotA, pd.nrays);
+  const XSlot sb = x_slot<SL>(blockIdx.x, slotB < SL ? slotB : 0, pd.nrays);
+  const bool actA = rA < R2;
+  const bool okB = slotB < SL && sb.valid;
+  const int spA = sa.self ? slotA : (slotA + H) % SL;
+  const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
+  const double sc = pd.inv_n;
+  uint32_t tab[KR::cnt];
+  double g2v[NPOS];
+  static_for<0, KR::cnt>([&](auto kk) {
+    constexpr int j = decltype(kk)::value;
+    constexpr int k = KR::lo + j;
+    const int xb = rA + R2 * k - pd.xlo;
+    tab[j] = (actA && sa.valid && xb >= 0 && xb < pd.nxb) ? __ldg(&pd.gtab[(size_t)xb * pd.nrp + sa.ray]) : kNoPW;
+    if constexpr (k < C0) {
+      if (!(tab[j] & kNegPW)) tab[j] = kNoPW;
+    }
+    if constexpr (k >= C0) {
+      g2v[k - C0] = (tab[j] != kNoPW && !(tab[j] & kNegPW)) ? pd.tpiba2 * __ldg(&pd.hg[tab[j]]) : 0.0;
+    }
+  });
+  // x-major role: element k of the first (radix-R2) pass is x = pB + R1*k
+  cplx nv[R2];
+  auto fetch = [&](int pair) {
+    const cplx* s = T1 + (size_t)pair * t1_pair + (size_t)(okB ? sb.ray : 0) * B;
+    static_for<0, R2>([&](auto kk) {
+      constexpr int k = decltype(kk)::value;
+      const int x = pB + R1 * k;
+      nv[k] = okB ? ld_stream(&s[(size_t)(x / B) * pd.nrays * B + (x % B)]) : mk(0.0, 0.0);
+    });
+  };
+  if (slotB < SL && p0 < p1) fetch(p0);
+  for (int pair = p0; pair < p1; ++pair) {
+    const int s1 = __ldg(&pr.st1[pair]), s2 = __ldg(&pr.st2[pair]);
+    if (actA) {
+      // stage the coefficients the unpack of this pair needs (own slots only: no barrier involved)
+      const cplx* a1 = c0 + (size_t)s1 * ldc;
+      const cplx* a2 = c0 + (size_t)(s2 < 0 ? s1 : s2) * ldc;
+      const cplx* o1 = c2 + (size_t)s1 * ldc;
+      const cplx* o2 = c2 + (size_t)(s2 < 0 ? s1 : s2) * ldc;
+      static_for<C0, KR::hi>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        constexpr int j = k - KR::lo;
+        if (tab[j] != kNoPW && !(tab[j] & kNegPW)) {
+          const int o = (k - C0) * NA + tidA;
+          cp_async16(&CS[0 * NPOS * NA + o], a1 + tab[j]);
+          if (s2 >= 0) cp_async16(&CS[1 * NPOS * NA + o], a2 + tab[j]);
+          if constexpr (ACC) {
+            cp_async16(&CS[2 * NPOS * NA + o], o1 + tab[j]);
+            if (s2 >= 0) cp_async16(&CS[3 * NPOS * NA + o], o2 + tab[j]);
+          }
+        }
+      });
+      cp_async_commit();
+    }
+    if (slotB < SL) {
+      cplx v[R2];
+      static_for<0, R2>([&](auto kk) { v[decltype(kk)::value] = nv[decltype(kk)::value]; });
+      // forward transform uses the mirrored factorisation (R2 first, then R1)
+      pass_a_st<R2, R1, false, 0, R2>(v, pB, pd.tw1, [&](int p, cplx o) { SX[(p * SL + slotB) * P1 + pB] = o; });
+      if (pair + 1 < p1) fetch(pair + 1);
+    }
+    __syncthreads();
+    cplx up[NPOS];  // my outputs at the positions that can hold +G
+    if (actA) {
+      cplx u[R1];
+      static_for<0, R1>([&](auto aa) {
+        constexpr int a = decltype(aa)::value;
+        u[a] = SX[(rA * SL + slotA) * P1 + a];
+      });
+      dft<R1, false>(u);
+      static_for<KR::lo, KR::hi>([&](auto tt) {
+        constexpr int t = decltype(tt)::value;
+        constexpr int j = t - KR::lo;
+        const cplx w = cscale(u[t], sc);
+        if constexpr (t >= C0) up[t - C0] = w;
+        if (tab[j] != kNoPW && (tab[j] & kNegPW)) {
+          // hand FFT[V psi](-G) to the owner of the +G position (n1 - x, mirror ray)
+          const int xm = pd.n1 - (rA + R2 * t);
+          EX[(xm / R2 - C0) * NA + (xm % R2) * SL + spA] = w;
+        }
+      });
+    }
+    __syncthreads();
+    if (actA) {
+      cp_async_wait_all();
+      const double fi = __ldg(&pr.ca[pair]), fip1 = __ldg(&pr.cb[pair]);
+      static_for<C0, KR::hi>([&](auto tt) {
+        constexpr int t = decltype(tt)::value;
+        constexpr int j = t - KR::lo;
+        const uint32_t ig = tab[j];
+        if (ig != kNoPW && !(ig & kNegPW)) {
+          const int o = (t - C0) * NA + tidA;
+          const cplx psin = up[t - C0];
+          // G = 0 is its own partner (vpsi_utils.mod.F90:655-671 reads psi(nzhs) and psi(indzs), the same element)
+          const bool selfpos = sa.self && 2 * (rA + R2 * t) == pd.n1;
+          const cplx psii = selfpos ? psin : EX[o];
+          const cplx a = CS[0 * NPOS * NA + o];
+          const cplx fp = cadd(psin, psii);
+          const cplx fm = csub(psin, psii);
+          const double g2 = g2v[t - C0];
+          cplx r1 = mk(-fi * (g2 * a.x + fp.x), -fi * (g2 * a.y + fm.y));
+          if constexpr (ACC) r1 = cadd(r1, CS[2 * NPOS * NA + o]);
+          c2[(size_t)s1 * ldc + ig] = r1;
+          if (s2 >= 0) {
+            const cplx bq = CS[1 * NPOS * NA + o];
+            cplx r2 = mk(-fip1 * (g2 * bq.x + fp.y), -fip1 * (g2 * bq.y - fm.x));
+            if constexpr (ACC) r2 = cadd(r2, CS[3 * NPOS * NA + o]);
+            c2[(size_t)s2 * ldc + ig] = r2;
+          }
+        }
+      });
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // y and z passes.  Common structure: a block owns B consecutive x (one 128-byte row per (y|z)
 // index) and loops over several packed pairs.  The band elements of the NEXT pair are fetched
 // into registers right after the first radix pass of the current pair, so their L2/HBM latency is

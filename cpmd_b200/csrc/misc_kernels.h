@@ -50,6 +50,32 @@ CPB_GLOBAL k_kin_energy(const cplx* CPB_RESTRICT c0, long ldc, int first_state, 
   }
 }
 
+// Last step of the kin_energy / dotp sums that k_x_inv_m accumulates while it gathers the coefficients:
+// block p adds the nbx block partials part[(p*nbx + bx)*4 + q] of pair p in a fixed order (bit-stable)
+// and writes them where the host expects k_kin_energy's chunk 0 of the pair's states:
+// out[((st - first)*kKinChunks + 0)*2 + {0: sum hg |c|^2, 1: dotp}], q = 0,1 -> st1, q = 2,3 -> st2.
+// The other chunks of `out` were zeroed by the caller.  grid = pairs, block = 128
+CPB_GLOBAL k_kin_reduce(const double* CPB_RESTRICT part, int nbx, PairDev pr, int first_state,
+                        double* CPB_RESTRICT out) {
+  CPB_DYN_SMEM(double, red);  // 4*128
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.x;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int bx = tid; bx < nbx; bx += 128)
+    for (int q = 0; q < 4; ++q) s[q] += part[((size_t)pair * nbx + bx) * 4 + q];
+  for (int q = 0; q < 4; ++q) red[q * 128 + tid] = s[q];
+  __syncthreads();
+  for (int k = 64; k > 0; k >>= 1) {
+    if (tid < k)
+      for (int q = 0; q < 4; ++q) red[q * 128 + tid] += red[q * 128 + tid + k];
+    __syncthreads();
+  }
+  if (tid < 4) {
+    const int st = tid < 2 ? pr.st1[pair] : pr.st2[pair];
+    if (st >= 0) out[((size_t)(st - first_state) * kKinChunks) * 2 + (tid & 1)] = red[tid * 128];
+  }
+}
+
 // sum of rho over the padded array (pads are zero): per-block partials, fixed order. block = 256
 CPB_GLOBAL k_sum(const double* CPB_RESTRICT a, size_t n, double* CPB_RESTRICT partial) {
   CPB_DYN_SMEM(double, red);

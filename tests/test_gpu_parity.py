@@ -243,7 +243,10 @@ def test_lsd_device_and_host(dev, n, nstate, nsup, mb):
 
 
 def test_psi_keep_reuse_device(dev):
-    """CPB_PSI_KEEP / CPB_PSI_REUSE on the device entry points: bit-identical, fewer launches."""
+    """CPB_PSI_KEEP / CPB_PSI_REUSE on the device entry points: same result, fewer launches.  rhoofr's
+    gather kernel is the instantiation that also accumulates kin_energy (k_x_inv_m<KIN>), vpsi's is not, so
+    the cached y-pass output and the recomputed one may differ in the last bit (FMA contraction is chosen
+    per instantiation): equal to 1e-14, and each path is bit-stable on its own."""
     n, ns = 64, 12
     d = synthetic.make_inputs(n, ns, f_pattern="mixed")
     plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
@@ -261,7 +264,13 @@ def test_psi_keep_reuse_device(dev):
     b = 0.5 * c0
     n0 = plan.launch_count
     plan.vpsi_dev(c0, b, d["f"], v, flags=lib.CPB_PSI_REUSE)
-    assert torch.equal(a, b) and plan.launch_count - n0 < full
+    assert plan.launch_count - n0 < full
+    err = (a - b).abs().max().item() / a.abs().max().item()
+    assert err < 1e-14, err
+    plan.rhoofr_dev(c0, d["f"], rho_k, flags=lib.CPB_PSI_KEEP)
+    b2 = 0.5 * c0
+    plan.vpsi_dev(c0, b2, d["f"], v, flags=lib.CPB_PSI_REUSE)
+    assert torch.equal(b, b2)                      # bit-stable
 
 
 # ---------------------------------------------------------------------------------------------
