@@ -107,6 +107,7 @@ struct cpb_plan {
   const void* psi_key_ptr = nullptr;
   long psi_key[5] = {0, 0, 0, 0, 0};  // ld, nstate, ngroups, my_group, nsup
   double prologue_pairs = 0.25;  // block prologue cost in pair-times (pairs_per_group model)
+  double prologue_pairs_x = 1.0; // same for the mirror-pair x kernels (position tables + hg per block; CPB_PROLOGUE_X)
   int x_sub = 32;         // pairs per forward x-pass sub-batch (measured: fewer launches beat L2 residency of G, profiles/r01g_notes.txt)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
@@ -370,8 +371,8 @@ void resolve_spans(cpb_plan* p) {
 // ceil(blocks / slots) waves, each lasting (pairs per block + block prologue) pair-times: pick the
 // group count that minimises that product.  Longer loops amortise the prologue and keep the
 // prefetch pipeline full; more groups cut the cost of the last, partially filled wave.
-int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group, int blocks_per_sm) {
-  const double prologue = p->prologue_pairs;
+int pairs_per_group(const cpb_plan* p, int npair, int blocks_per_pair_group, int blocks_per_sm, double prologue = -1.0) {
+  if (prologue < 0.0) prologue = p->prologue_pairs;
   const long slots = (long)p->n_sm * std::max(blocks_per_sm, 1);
   int best = npair;
   double best_cost = 1e300;
@@ -405,8 +406,8 @@ void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, co
   Timed t(p, st, CPB_K_X_INV);
   if (p->mirror && !p->kpt_mode) {
     double* kin = p->kin_cur ? p->kin_cur + (size_t)off * p->nbx_m * 4 : nullptr;
-    p->kx->x_inv_m(st, c0, ldc, w.T1, p->pd, prb, nb, pairs_per_group(p, nb, p->nbx_m, p->kx->x_inv_m_blocks),
-                   p->half_x, kin, p->geq0);
+    p->kx->x_inv_m(st, c0, ldc, w.T1, p->pd, prb, nb,
+                   pairs_per_group(p, nb, p->nbx_m, p->kx->x_inv_m_blocks, p->prologue_pairs_x), p->half_x, kin, p->geq0);
     return;
   }
   p->kx->x_inv(st, c0, ldc, w.T1, p->kpt_mode ? p->pdk : p->pd, prb, nb,
@@ -447,8 +448,8 @@ void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, lo
   if (p->mirror && !p->kpt_mode) {
     // Gamma point: forward x pass fused with the unpack (no band-ray storage, one launch per batch)
     Timed t(p, st, CPB_K_X_FWD);
-    p->kx->x_fwd_m(st, w.T1, c0, c2, ldc, p->pd, prb, nb, pairs_per_group(p, nb, p->nbx_m, p->kx->x_fwd_m_blocks),
-                   p->half_x, accumulate);
+    p->kx->x_fwd_m(st, w.T1, c0, c2, ldc, p->pd, prb, nb,
+                   pairs_per_group(p, nb, p->nbx_m, p->kx->x_fwd_m_blocks, p->prologue_pairs_x), p->half_x, accumulate);
     return;
   }
   for (int o = 0; o < nb; o += p->x_sub) {
@@ -937,6 +938,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->t1_pair = (size_t)p->nxt * nrays * Bx;
     if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("CPB_PROLOGUE")) p->prologue_pairs = std::max(0.0, std::atof(e));
+    if (const char* e = std::getenv("CPB_PROLOGUE_X")) p->prologue_pairs_x = std::max(0.0, std::atof(e));
     p->x_sub = std::min(p->x_sub, p->max_batch);
     p->g_pair = (size_t)nxb * nrp;
     p->t2_pair = (size_t)p->nxt * n2 * nzb * Bx;

@@ -416,10 +416,12 @@ struct XMCfg {
   static constexpr int NA = C::NA;
   static constexpr int NW = (C::NT + 31) / 32;
   // inverse: exchange + twiddles + 2 gather stages [state][NPOS][NA] (+ reduction scratch with KIN)
+  // (+ the block's pair descriptors: 2 ints + 2 doubles per pair)
   static constexpr size_t SMEM_INV = (size_t)(C::SX_ELEMS + C::N + 2 * 2 * NPOS * NA) * sizeof(cplx) +
-                                     (size_t)(4 * NA + 2 * 4 * 8) * sizeof(double);
-  // forward: exchange + partner exchange [NPOS][NA] + staged c0 / c2 values [4][NPOS][NA]
-  static constexpr size_t SMEM_FWD = (size_t)(C::SX_ELEMS + NPOS * NA + 4 * NPOS * NA) * sizeof(cplx);
+                                     (size_t)(4 * NA + 2 * 4 * 8 + 3 * kMaxGroup) * sizeof(double);
+  // forward: exchange + twiddles + partner exchange [NPOS][NA] + staged c0 / c2 values [4][NPOS][NA]
+  static constexpr size_t SMEM_FWD = (size_t)(C::SX_ELEMS + C::N + NPOS * NA + 4 * NPOS * NA) * sizeof(cplx) +
+                                     (size_t)(3 * kMaxGroup) * sizeof(double);
   static constexpr int MINB_INV = (C::NT <= 128) ? ((C::RM <= 16) ? 4 : 3) : 2;
   static constexpr int MINB_FWD = (C::NT <= 128) ? 3 : 2;
 };
@@ -456,9 +458,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   cplx* ST = TW + N;                                     // [buf][state][NPOS][NA]
   double* RED = reinterpret_cast<double*>(ST + 2 * 2 * NPOS * NA);   // [4][NA]
   double* RED2 = RED + 4 * NA;                           // [2][4][8], alternating per pair
+  int* PS1 = reinterpret_cast<int*>(RED2 + 2 * 4 * 8);   // the block's pair descriptors [kMaxGroup] each
+  int* PS2 = PS1 + kMaxGroup;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  for (int i = tid; i < p1 - p0; i += NT) {
+    PS1[i] = __ldg(&pr.st1[p0 + i]);
+    PS2[i] = __ldg(&pr.st2[p0 + i]);
+  }
 #if CPB_X_ROT
   const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;  // see k_x_inv
 #else
@@ -489,7 +497,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
     }
   });
   auto gather = [&](int pair, int buf) {
-    const int s1 = __ldg(&pr.st1[pair]), s2 = __ldg(&pr.st2[pair]);
+    const int s1 = PS1[pair - p0], s2 = PS2[pair - p0];
     const cplx* c1p = c0 + (size_t)s1 * ldc;
     const cplx* c2p = c0 + (size_t)(s2 < 0 ? s1 : s2) * ldc;
     cplx* st = ST + (size_t)buf * (2 * NPOS * NA);
@@ -503,6 +511,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
     });
     cp_async_commit();
   };
+  __syncthreads();  // pair descriptors visible
   if (actA && p0 < p1) gather(p0, 0);
   for (int pair = p0; pair < p1; ++pair) {
     const int buf = (pair - p0) & 1;
@@ -510,7 +519,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
     __syncthreads();  // the stage of this pair is complete and visible to the partner threads; SX and TW are free / ready
     if (actA) {
       if (pair + 1 < p1) gather(pair + 1, buf ^ 1);      // the other stage was last read one iteration ago
-      const bool two = __ldg(&pr.st2[pair]) >= 0;
+      const bool two = PS2[pair - p0] >= 0;
       const cplx* st = ST + (size_t)buf * (2 * NPOS * NA);
       double sk1 = 0.0, sd1 = 0.0, sk2 = 0.0, sd2 = 0.0;
       cplx v[R1];
@@ -616,11 +625,23 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   constexpr int NT = C::NT, P1 = C::P1, NA = C::NA, H = M::H, C0 = M::C0, NPOS = M::NPOS;
   CPB_DYN_SMEM(cplx, S);
   cplx* SX = S;
-  cplx* EX = S + C::SX_ELEMS;         // [NPOS][NA]: FFT[V psi] at the -G partner of my +G positions
+  cplx* TW = S + C::SX_ELEMS;
+  cplx* EX = TW + C::N;               // [NPOS][NA]: FFT[V psi] at the -G partner of my +G positions
   cplx* CS = EX + NPOS * NA;          // [4][NPOS][NA]: c0(ig, s1), c0(ig, s2), c2(ig, s1), c2(ig, s2)
+  double* PCA = reinterpret_cast<double*>(CS + 4 * NPOS * NA);   // the block's pair descriptors [kMaxGroup] each
+  double* PCB = PCA + kMaxGroup;
+  int* PS1 = reinterpret_cast<int*>(PCB + kMaxGroup);
+  int* PS2 = PS1 + kMaxGroup;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  for (int i = tid; i < p1 - p0; i += NT) {
+    PS1[i] = __ldg(&pr.st1[p0 + i]);
+    PS2[i] = __ldg(&pr.st2[p0 + i]);
+    PCA[i] = __ldg(&pr.ca[p0 + i]);
+    PCB[i] = __ldg(&pr.cb[p0 + i]);
+  }
+  for (int i = tid; i < C::N; i += NT) TW[i] = pd.tw1[i];
 #if CPB_X_ROT
   const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;  // see k_x_inv
 #else
@@ -660,8 +681,9 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
     });
   };
   if (slotB < SL && p0 < p1) fetch(p0);
+  __syncthreads();  // pair descriptors and twiddles visible
   for (int pair = p0; pair < p1; ++pair) {
-    const int s1 = __ldg(&pr.st1[pair]), s2 = __ldg(&pr.st2[pair]);
+    const int s1 = PS1[pair - p0], s2 = PS2[pair - p0];
     if (actA) {
       // stage the coefficients the unpack of this pair needs (own slots only: no barrier involved)
       const cplx* a1 = c0 + (size_t)s1 * ldc;
@@ -687,7 +709,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
       cplx v[R2];
       static_for<0, R2>([&](auto kk) { v[decltype(kk)::value] = nv[decltype(kk)::value]; });
       // forward transform uses the mirrored factorisation (R2 first, then R1)
-      pass_a_st<R2, R1, false, 0, R2>(v, pB, pd.tw1, [&](int p, cplx o) { SX[(p * SL + slotB) * P1 + pB] = o; });
+      pass_a_st<R2, R1, false, 0, R2, true>(v, pB, TW, [&](int p, cplx o) { SX[(p * SL + slotB) * P1 + pB] = o; });
       if (pair + 1 < p1) fetch(pair + 1);
     }
     __syncthreads();
@@ -714,7 +736,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
     __syncthreads();
     if (actA) {
       cp_async_wait_all();
-      const double fi = __ldg(&pr.ca[pair]), fip1 = __ldg(&pr.cb[pair]);
+      const double fi = PCA[pair - p0], fip1 = PCB[pair - p0];
       static_for<C0, KR::hi>([&](auto tt) {
         constexpr int t = decltype(tt)::value;
         constexpr int j = t - KR::lo;
