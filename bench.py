@@ -225,6 +225,39 @@ def cpu_baseline(args):
             "probe_band_ffts_per_s": rates}
 
 
+def reference_gpu(args):
+    """The reference's OWN GPU path on this B200 (rank 0, N=1 only; bench-only, see oracle/ref_gpu_driver.cu):
+    its CUDA sources compiled by nvcc where they lie, cuFFT plans per cp_cufft_utils.mod.F90:336-372, stage
+    order and host round trips of fftcu_methods.mod.F90 with the shipped use_cpu_unpack_x2y = use_cpu_pack_y2x
+    = .TRUE., one task / device / stream, wavefunctions resident on the device (cp_cuwfn).  A bounded
+    sample of the workload; `device_scatter` is the variant behind use_cpu_* = .FALSE."""
+    from oracle import cpmd_oracle as orc
+    from oracle import ref_gpu
+
+    if ref_gpu.load() is None:
+        return {"unavailable": "oracle/_ref/libref_gpu.so not built (needs /root/reference at build time)"}
+    n = args.mesh
+    ns = min(args.ref_gpu_sample_states, args.states)
+    geo = orc.make_geometry(n)
+    c0, f, v = orc.synthetic_inputs(geo, ns, seed=1234 + n + 7 * args.states)
+    ref = ref_gpu.RefGpu(geo, 1.0, 1.0)
+    out = {"unit": UNIT, "kind": "reference code: src/cuuser_utils.cu + cuuser_utils_kernels.cu + cuFFT, stage order of "
+                                 "fftcu_methods.mod.F90 (4 host<->device copies per 3-D FFT), 1 device, 1 stream",
+           "sample": f"{ns} of {args.states} states, mesh {n}^3, rhoofr+vpsi"}
+    for key, scatter in (("value", False), ("value_device_scatter", True)):
+        ref.rhoofr(c0[:2], f[:2], device_scatter=scatter)             # plans, page faults
+        t0 = time.perf_counter()
+        rho = ref.rhoofr(c0, f, device_scatter=scatter)
+        c2 = ref.vpsi(c0, np.zeros_like(c0), f, v, device_scatter=scatter)
+        dt = time.perf_counter() - t0
+        out[key] = 3.0 * ns / dt
+        npts = float(n) ** 3
+        out["charge_identity_ok"] = bool(abs(rho.sum() / npts - 2.0 * ns) < 1e-8 * ns)
+        del c2
+    ref.close()
+    return out
+
+
 def widened_rows(args, dev, plan, c0, f_block, v, timed):
     """Measurements for the SURVEY 8(f) rows built next to the hot path (N=1 only; device-resident,
     CUDA events, 3 warm-up + 5 timed calls each): the local part of vofrho on the density cutoff,
@@ -637,6 +670,10 @@ def run_ours(args, rank, world, local):
         line["sweep"] = sweep
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
+        try:
+            line["reference_gpu"] = reference_gpu(args)
+        except Exception as e:      # a baseline leg must not take the bench line down
+            line["reference_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
     _emit(line)
 
 
@@ -673,6 +710,8 @@ def main():
                     help="states per step of the --impl reference arm (bounded sample of the workload)")
     ap.add_argument("--cpu-sample-states", type=int, default=256,
                     help="states of the cpu_baseline leg (about 10-30 s of CPU work)")
+    ap.add_argument("--ref-gpu-sample-states", type=int, default=32,
+                    help="states of the reference_gpu leg (the reference's own cuFFT path, bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the widened-row measurements (vofrho, k-points, tau)")
     args = ap.parse_args()
