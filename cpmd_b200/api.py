@@ -369,6 +369,38 @@ class Plan:
                                             _ptr(vtau), ngroups, my_group, 0, _stream_ptr(stream)))
         return c2
 
+    # -- Hartree-Fock exchange (hfx_old, Gamma point, no LSD, no screening) -------------------------
+    def hfx_dev(self, dens_plan, c0, c2, f, scgx, pfl=0.25, nstate=None, stream=None):
+        """``cpb_hfx_dev``: self = the wavefunction plan, ``dens_plan`` = the plan of the pair-density FFT set
+        (same mesh), ``scgx`` its Coulomb kernel (device, dens_plan.ngw doubles).  c2 += C2_hfx; returns
+        (ehfx, vhfx) (hfx_utils.mod.F90:80-965)."""
+        nstate, ld = self._c0_args(c0, nstate)
+        f = self._f_arg(f, nstate)
+        if tuple(c2.shape) != tuple(c0.shape):
+            raise ValueError("c2 must have the shape of c0")
+        if _numel(scgx) < dens_plan.ngw:
+            raise ValueError("scgx needs one entry per vector of the pair-density set")
+        e, v = C.c_double(), C.c_double()
+        self._check(self._L.cpb_hfx_dev(self._h, dens_plan._h, _ptr(c0), _ptr(c2), ld, nstate, f.ctypes.data, _ptr(scgx),
+                                        float(pfl), C.byref(e), C.byref(v), 0, _stream_ptr(stream)))
+        return e.value, v.value
+
+    def hfx(self, dens_plan, c0, c2, f, scgx, pfl=0.25, nstate=None):
+        """``cpb_hfx`` (host arrays): c2 (in/out) += C2_hfx; returns (ehfx, vhfx)."""
+        c0 = _as_host(c0, np.complex128)
+        c2h = _as_host(c2, np.complex128)
+        if c2h.shape != c0.shape:
+            raise ValueError("c2 must have the shape of c0")
+        nstate, ld = self._c0_args(c0, nstate)
+        f = self._f_arg(f, nstate)
+        scgx = np.ascontiguousarray(scgx, dtype=np.float64)
+        if scgx.size < dens_plan.ngw:
+            raise ValueError("scgx needs one entry per vector of the pair-density set")
+        e, v = C.c_double(), C.c_double()
+        self._check(self._L.cpb_hfx(self._h, dens_plan._h, c0.ctypes.data, c2h.ctypes.data, ld, nstate, f.ctypes.data,
+                                    scgx.ctypes.data, float(pfl), C.byref(e), C.byref(v), 0))
+        return e.value, v.value
+
     # -- host-array forms of the k-point / meta-GGA entry points (the Fortran drop-in path) ----------
     def rhoofr_kpt(self, c0, f, wk, hgkp, hgkm, rhoe=None, nstate=None, ngroups=1, my_group=0, accumulate=False):
         c0 = _as_host(c0, np.complex128)

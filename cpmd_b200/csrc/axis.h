@@ -44,7 +44,7 @@ struct AxisKernels {
                  int ppg, bool half);
   // dense transforms (real fields on the density-cutoff sphere): z passes with phasen
   void (*z_fwd_real)(cudaStream_t, const double* fre, const double* fim, cplx* T2, const PlanDev&, int xt0, int nxc,
-                     bool half);
+                     bool half, const double* mul, double scale);
   void (*z_inv_real)(cudaStream_t, const cplx* T2, double* ore, double* oim, const PlanDev&, int xt0, int nxc,
                      bool acc, bool half);
   int yz_blocks_per_sm;  // occupancy the y/z kernels are compiled for

@@ -191,15 +191,15 @@ void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, in
 
 template <bool HALF>
 void z_fwd_real_t(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0,
-                  int nxc) {
+                  int nxc, const double* mul, double scale) {
   auto k = k_z_fwd_real<R1, R2, B, HALF>;
   allow_smem(k, kSmemYZ);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, fre, fim, T2, pd, xt0);
+  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, fre, fim, T2, pd, xt0, mul, scale);
 }
 void z_fwd_real(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0, int nxc,
-                bool half) {
-  if (half) z_fwd_real_t<true>(st, fre, fim, T2, pd, xt0, nxc);
-  else z_fwd_real_t<false>(st, fre, fim, T2, pd, xt0, nxc);
+                bool half, const double* mul, double scale) {
+  if (half) z_fwd_real_t<true>(st, fre, fim, T2, pd, xt0, nxc, mul, scale);
+  else z_fwd_real_t<false>(st, fre, fim, T2, pd, xt0, nxc, mul, scale);
 }
 
 template <bool HALF>

@@ -1232,7 +1232,7 @@ void run_dense_fw(cpb_plan* p, const double* f, int nf, cplx* g, long ld, cudaSt
   const double* fim = nf == 2 ? f + p->nnr1() : nullptr;
   for (int xt0 = 0; xt0 < p->nxt; xt0 += p->chunk_xt) {
     const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
-    { Timed t(p, st, CPB_K_DENSE); p->kz->z_fwd_real(st, f, fim, w.T2, p->pd, xt0, nxc, p->half_z); }
+    { Timed t(p, st, CPB_K_DENSE); p->kz->z_fwd_real(st, f, fim, w.T2, p->pd, xt0, nxc, p->half_z, nullptr, 1.0); }
     { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, w.T2, w.T1, p->pd, 1, xt0, nxc, 1, p->half_y); }
   }
   { Timed t(p, st, CPB_K_X_FWD); p->kx->x_fwd(st, w.T1, w.G, p->pd, 1, 1, p->half_x); }
@@ -1661,6 +1661,191 @@ int cpb_vtaupsi_dev(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld, int 
                 count_chan0(pairs), gk_dev, vtau_dev, vtau_dev + p->nnr1(), st);
     rt::sync(st);
     resolve_spans(p);
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(CPB_ERR_NOMEM, "out of host memory");
+  }
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Hartree-Fock exchange: hfx_old with func1%mhfx = 1 at the Gamma point, no LSD, no
+// screening (hfx_utils.mod.F90:80-965), assembled from the transforms above
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// inverse transform of the packed "pairs" described by pr on plan p: gather + x + y into ws[0].T2
+void hfx_xy_inv(cpb_plan* p, const cplx* g, long ldg, const PairDev& pr, int nb, cudaStream_t st) {
+  cpb_plan::WorkSpace& w = p->ws[0];
+  {
+    Timed t(p, st, CPB_K_X_INV);
+    if (p->mirror)
+      p->kx->x_inv_m(st, g, ldg, w.T1, p->pd, pr, nb, nb, p->half_x, nullptr, p->geq0);
+    else
+      p->kx->x_inv(st, g, ldg, w.T1, p->pd, pr, nb, nb, p->half_x);
+  }
+  Timed t(p, st, CPB_K_Y_INV);
+  p->ky->y_inv(st, w.T1, w.T2, p->pd, nb, 0, p->nxt, nb, p->half_y);
+}
+
+// forward transform of one real-space field scale * mul * (fre + i fim) on plan p into the band-ray storage ws[0].G
+void hfx_fwd(cpb_plan* p, const double* fre, const double* fim, const double* mul, double scale, cudaStream_t st) {
+  cpb_plan::WorkSpace& w = p->ws[0];
+  { Timed t(p, st, CPB_K_DENSE); p->kz->z_fwd_real(st, fre, fim, w.T2, p->pd, 0, p->nxt, p->half_z, mul, scale); }
+  { Timed t(p, st, CPB_K_Y_FWD); p->ky->y_fwd(st, w.T2, w.T1, p->pd, 1, 0, p->nxt, 1, p->half_y); }
+  { Timed t(p, st, CPB_K_X_FWD); p->kx->x_fwd(st, w.T1, w.G, p->pd, 1, 1, p->half_x); }
+}
+
+struct DevBuf {  // RAII device allocation
+  void* p = nullptr;
+  explicit DevBuf(size_t bytes) : p(rt::dmalloc(bytes)) {}
+  ~DevBuf() { rt::dfree(p); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+}  // namespace
+
+extern "C" {
+
+int cpb_hfx_dev(cpb_plan* pw, cpb_plan* pdn, const void* c0_dev, void* c2_dev, long ld, int nstate, const double* f,
+                const double* scgx_dev, double pfl, double* ehfx, double* vhfx, unsigned flags, void* stream) {
+  (void)flags;
+  if (!pw || !pdn) return fail(CPB_ERR_INVALID, "null plan");
+  if (int e = check_common(pw, c0_dev, ld, nstate, f, 1, 0)) return e;
+  if (!c2_dev || !scgx_dev) return fail(CPB_ERR_INVALID, "null c2 or scgx");
+  for (int d = 0; d < 3; ++d)
+    if (pw->nr[d] != pdn->nr[d] || pw->kr[d] != pdn->kr[d])
+      return fail(CPB_ERR_INVALID, "the wavefunction plan and the pair-density plan must share the mesh");
+  if (pw->device != pdn->device) return fail(CPB_ERR_INVALID, "the two plans live on different devices");
+  if (pw->chunk_xt != pw->nxt || pdn->chunk_xt != pdn->nxt)
+    return fail(CPB_ERR_UNSUPPORTED, "cpb_hfx_dev needs unchunked y/z passes (CPB_CHUNK_XT unset)");
+  try {
+    rt::set_device(pw->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cplx* c0 = (const cplx*)c0_dev;
+    cplx* c2 = (cplx*)c2_dev;
+    const size_t nnr1 = pw->nnr1();
+    const int jhg = pdn->ngw;
+    pw->psi_valid = false;
+    std::vector<int> occ;
+    for (int i = 0; i < nstate; ++i)
+      if (f[i] >= 1.0e-6) occ.push_back(i);  // hfx_utils.mod.F90:474
+    const int nocc = (int)occ.size();
+    double e_total = 0.0;
+    if (nocc > 0) {
+      DevBuf rbuf((size_t)nocc * nnr1 * sizeof(double));   // psi_i(r) of every occupied state (rswfx)
+      DevBuf vrbuf(2 * nnr1 * sizeof(double));              // vpotr of the two partners of a packet
+      DevBuf vgbuf(2 * (size_t)jhg * sizeof(cplx));         // vpotg
+      DevBuf ebuf(kSumBlocks * sizeof(double));
+      DevBuf dbuf(4 * sizeof(int) + 4 * sizeof(double));
+      double* R = (double*)rbuf.p;
+      double* vr = (double*)vrbuf.p;
+      cplx* vg = (cplx*)vgbuf.p;
+      double* eacc = (double*)ebuf.p;
+      rt::dzero(eacc, kSumBlocks * sizeof(double), st);
+      rt::dzero(R, (size_t)nocc * nnr1 * sizeof(double), st);   // pads
+      rt::dzero(vr, 2 * nnr1 * sizeof(double), st);
+      // descriptors of the two packings of the pair-density plan: columns (0, 1) and (0, -)
+      {
+        const int hs[4] = {0, 0, 1, -1};
+        const double hz[4] = {0, 0, 0, 0};
+        int* di = (int*)dbuf.p;
+        double* dd = (double*)(di + 4);
+        rt::h2d(di, hs, sizeof hs, st);
+        rt::h2d(dd, hz, sizeof hz, st);
+        rt::sync(st);  // hs / hz live on this stack frame
+      }
+      int* di = (int*)dbuf.p;
+      double* dd = (double*)(di + 4);
+      PairDev two, one;
+      two.st1 = di;
+      two.st2 = di + 2;
+      two.ca = dd;
+      two.cb = dd + 2;
+      one = offset_pairs(two, 1);
+      // ---- real-space states, two per transform (set_psi_2_states_g + invfftn, :296-318)
+      {
+        std::vector<PairHost> pairs;
+        for (int i = 0; i < nocc; i += 2) {
+          PairHost q;
+          q.s1 = occ[i];
+          q.s2 = i + 1 < nocc ? occ[i + 1] : -1;
+          pairs.push_back(q);
+        }
+        const std::vector<double> z(pairs.size(), 0.0);
+        const PairDev pr = upload_pairs(pw, pairs, z, z, st);
+        cpb_plan::WorkSpace& w = pw->ws[0];
+        for (int off = 0; off < (int)pairs.size(); off += pw->max_batch) {
+          const int nb = std::min(pw->max_batch, (int)pairs.size() - off);
+          hfx_xy_inv(pw, c0, ld, offset_pairs(pr, off), nb, st);
+          for (int i = 0; i < nb; ++i) {
+            const int k = 2 * (off + i);
+            Timed t(pw, st, CPB_K_DENSE);
+            pw->kz->z_inv_real(st, w.T2 + (size_t)i * pw->t2_pair, R + (size_t)k * nnr1,
+                               k + 1 < nocc ? R + (size_t)(k + 1) * nnr1 : nullptr, pw->pd, 0, pw->nxt, false, pw->half_z);
+          }
+        }
+      }
+      // ---- pair terms: state ia with itself (hfxaa = hfxab with half the prefactor) and with every later
+      // occupied state, two partners per pair-density transform (hfxab2, :704-745)
+      for (int a = 0; a < nocc; ++a) {
+        const int ia = occ[a];
+        for (int k = a; k < nocc; k += 2) {
+          const int b1 = k, b2 = k + 1 < nocc ? k + 1 : -1;
+          const double pf1 = pfl * f[ia] * f[occ[b1]] * (b1 == a ? 0.5 : 1.0);
+          const double pf2 = b2 >= 0 ? pfl * f[ia] * f[occ[b2]] : 0.0;
+          const double* ra = R + (size_t)a * nnr1;
+          hfx_fwd(pdn, R + (size_t)b1 * nnr1, b2 >= 0 ? R + (size_t)b2 * nnr1 : nullptr, ra, 1.0 / pw->omega, st);
+          {
+            Timed t(pdn, st, CPB_K_DENSE);
+            auto kc = k_hfx_coulomb;
+            CPB_LAUNCH(kc, dim3(kSumBlocks), dim3(256), 256 * sizeof(double), st, (const cplx*)pdn->ws[0].G, pdn->pd, scgx_dev,
+                       pf1, pf2, b2 >= 0 ? 1 : 0, pdn->geq0, vg, vg + jhg, eacc);
+          }
+          hfx_xy_inv(pdn, vg, jhg, b2 >= 0 ? two : one, 1, st);
+          {
+            Timed t(pdn, st, CPB_K_DENSE);
+            pdn->kz->z_inv_real(st, pdn->ws[0].T2, vr, b2 >= 0 ? vr + nnr1 : nullptr, pdn->pd, 0, pdn->nxt, false, pdn->half_z);
+          }
+          for (int j = 0; j < 2; ++j) {
+            const int b = j == 0 ? b1 : b2;
+            if (b < 0) continue;
+            hfx_fwd(pw, ra, R + (size_t)b * nnr1, vr + (size_t)j * nnr1, 1.0, st);
+            Timed t(pw, st, CPB_K_UNPACK);
+            auto ka = k_hfx_acc;
+            CPB_LAUNCH(ka, dim3((pw->ngw + 255) / 256), dim3(256), 0, st, (const cplx*)pw->ws[0].G, pw->pd,
+                       c2 + (size_t)ia * ld, c2 + (size_t)occ[b] * ld, b == a ? 1 : 0);
+          }
+        }
+      }
+      rt::check_last("hfx kernels");
+      ensure_red(pw, std::max(kSumBlocks, kKinChunks * nstate));
+      rt::d2h(pw->h_red, eacc, kSumBlocks * sizeof(double), st);
+      rt::sync(st);
+      for (int i = 0; i < kSumBlocks; ++i) e_total += pw->h_red[i];
+    }
+    if (ehfx) *ehfx = e_total * pw->omega;  // :905
+    if (vhfx) {
+      double v = 0.0;
+      if (nstate > 0) {
+        ensure_red(pw, std::max(kSumBlocks, kKinChunks * nstate));
+        auto kd = k_dotp;
+        Timed t(pw, st, CPB_K_KIN);
+        CPB_LAUNCH(kd, dim3(kKinChunks, nstate), dim3(256), 256 * sizeof(double), st, c0, (const cplx*)c2, ld, pw->ngw,
+                   pw->geq0, pw->d_red);
+        rt::d2h(pw->h_red, pw->d_red, (size_t)kKinChunks * nstate * sizeof(double), st);
+        rt::sync(st);
+        for (int i = 0; i < kKinChunks * nstate; ++i) v += pw->h_red[i];  // :907-909
+      }
+      *vhfx = v;
+    }
+    rt::sync(st);
+    resolve_spans(pw);
+    resolve_spans(pdn);
     return CPB_OK;
   } catch (const Error& e) {
     return fail(e.code, e.what());

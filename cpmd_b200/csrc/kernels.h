@@ -1174,11 +1174,13 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
 // centre used by the index maps to the origin.  One transform per call: no pair loop, plain
 // global loads.  grid = (x tiles of the chunk, n2), block = B * max(R1,R2)
 // ---------------------------------------------------------------------------------------------
-// forward: f(r) -> phasen -> z FFT (e^{-i...}) -> band of T2
+// forward: f(r) -> phasen -> z FFT (e^{-i...}) -> band of T2.  mul != nullptr: the field is scale * mul(r) *
+// (fre(r) + i fim(r)) - the pair densities psi_a psi_b / omega and the products v(r) (psi_a + i psi_b) of the
+// exact-exchange path (hfx_utils.mod.F90:1052-1063, 1085-1095) without a pass of their own
 template <int R1, int R2, int B, bool HALF>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
     k_z_fwd_real(const double* CPB_RESTRICT fre, const double* CPB_RESTRICT fim, cplx* CPB_RESTRICT T2, PlanDev pd,
-                 int xt0) {
+                 int xt0, const double* CPB_RESTRICT mul, double scale) {
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
   const int tid = threadIdx.x;
@@ -1196,7 +1198,12 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
       const int z = r + R1 * q;
       const size_t o = ((size_t)z * pd.kr2 + y) * pd.kr1 + x;
       const double sg = ((x + y + z) & 1) ? -1.0 : 1.0;
-      u[q] = xok ? mk(sg * fre[o], fim ? sg * fim[o] : 0.0) : mk(0.0, 0.0);
+      if (mul) {
+        const double m = xok ? sg * scale * mul[o] : 0.0;
+        u[q] = xok ? mk(m * fre[o], fim ? m * fim[o] : 0.0) : mk(0.0, 0.0);
+      } else {
+        u[q] = xok ? mk(sg * fre[o], fim ? sg * fim[o] : 0.0) : mk(0.0, 0.0);
+      }
     });
     pass_a<R2, R1, false>(u, r, pd.tw3, Sf, B);
   }

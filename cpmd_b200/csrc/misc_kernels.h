@@ -352,4 +352,88 @@ CPB_GLOBAL k_unpack_tau(const cplx* CPB_RESTRICT G, cplx* CPB_RESTRICT c2, long 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hartree-Fock exchange (hfx_utils.mod.F90:1034-1260), G side on the pair-density FFT set.
+// k_hfx_coulomb: the pair density (densities) from the band-ray storage of the dense forward transform -
+// one real field: rho(G) = P(+G); two packed as Re / Im: the +-G separation of k_gather_g - then
+// vpotg = -pf scgx rho (:1068) and the pair energy sum_G 4 Re(vpotg conj rho), G = 0 counted half (:1069-1071).
+// eacc[block] += the block's partial sum of both fields: a fixed launch order makes the total bit-stable.
+// block = 256
+// ---------------------------------------------------------------------------------------------
+CPB_GLOBAL k_hfx_coulomb(const cplx* CPB_RESTRICT G, PlanDev pd, const double* CPB_RESTRICT scgx, double pf1, double pf2,
+                         int two, int geq0, cplx* CPB_RESTRICT v1, cplx* CPB_RESTRICT v2, double* eacc) {
+  CPB_DYN_SMEM(double, red);  // 256
+  const int tid = threadIdx.x;
+  double e = 0.0;
+  for (int ig = blockIdx.x * 256 + tid; ig < pd.ngw; ig += gridDim.x * 256) {
+    const cplx pp = G[pd.gpos[ig]];
+    const double sc = scgx[ig];
+    const double w = (ig == 0 && geq0) ? 2.0 : 4.0;
+    if (!two) {
+      const cplx vg = cscale(pp, -pf1 * sc);
+      v1[ig] = vg;
+      e += w * (vg.x * pp.x + vg.y * pp.y);
+    } else {
+      const cplx pm = G[pd.gneg[ig]];
+      const cplx ra = mk(0.5 * (pp.x + pm.x), 0.5 * (pp.y - pm.y));
+      const cplx rb = mk(0.5 * (pp.y + pm.y), 0.5 * (pm.x - pp.x));
+      const cplx va = cscale(ra, -pf1 * sc), vb = cscale(rb, -pf2 * sc);
+      v1[ig] = va;
+      v2[ig] = vb;
+      e += w * (va.x * ra.x + va.y * ra.y) + w * (vb.x * rb.x + vb.y * rb.y);
+    }
+  }
+  red[tid] = e;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (tid < k) red[tid] += red[tid + k];
+    __syncthreads();
+  }
+  if (tid == 0) eacc[blockIdx.x] += red[0];
+}
+
+// k_hfx_acc: the decode of hfxab (hfx_utils.mod.F90:1097-1107) from the band-ray storage of the sparse forward
+// transform of v(r) (psi_a + i psi_b): c2b -= (Re fp, Im fm), c2a -= (Im fp, -Re fm), fp / fm = P(+G) +- P(-G).
+// same != 0 (the diagonal term, a == b): both updates go to the one column.  grid = ceil(ngw/256)
+CPB_GLOBAL k_hfx_acc(const cplx* CPB_RESTRICT G, PlanDev pd, cplx* c2a, cplx* c2b, int same) {
+  const int ig = blockIdx.x * 256 + threadIdx.x;
+  if (ig >= pd.ngw) return;
+  const cplx pp = G[pd.gpos[ig]], pm = G[pd.gneg[ig]];
+  const cplx fp = cadd(pp, pm), fm = csub(pp, pm);
+  if (same) {
+    const cplx a = c2a[ig];
+    c2a[ig] = mk(a.x - fp.x - fp.y, a.y - fm.y + fm.x);
+  } else {
+    const cplx b = c2b[ig], a = c2a[ig];
+    c2b[ig] = mk(b.x - fp.x, b.y - fm.y);
+    c2a[ig] = mk(a.x - fp.y, a.y + fm.x);
+  }
+}
+
+// dotp(c0_i, c2_i) per state (dotp_utils.mod.F90:26-53: weight 2, the real parts once at G = 0): per-chunk partials
+// out[st*kKinChunks + c], fixed order.  grid = (kKinChunks, states), block = 256
+CPB_GLOBAL k_dotp(const cplx* CPB_RESTRICT a, const cplx* CPB_RESTRICT b, long ld, int ngw, int geq0,
+                  double* CPB_RESTRICT out) {
+  CPB_DYN_SMEM(double, red);  // 256
+  const int tid = threadIdx.x;
+  const int st = blockIdx.y;
+  const int per = (ngw + kKinChunks - 1) / kKinChunks;
+  const int g0 = blockIdx.x * per;
+  const int g1 = (g0 + per < ngw) ? g0 + per : ngw;
+  const cplx* pa = a + (size_t)st * ld;
+  const cplx* pb = b + (size_t)st * ld;
+  double s = 0.0;
+  for (int ig = g0 + tid; ig < g1; ig += 256) {
+    const cplx x = pa[ig], y = pb[ig];
+    s += (ig == 0 && geq0) ? x.x * y.x : 2.0 * (x.x * y.x + x.y * y.y);
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (tid < k) red[tid] += red[tid + k];
+    __syncthreads();
+  }
+  if (tid == 0) out[(size_t)st * kKinChunks + blockIdx.x] = red[0];
+}
+
 }  // namespace cpb

@@ -124,6 +124,10 @@ SYMBOLS = {
                                  C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
     "cpb_vtaupsi_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "cpb_hfx_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
+    "cpb_hfx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p,
+                          C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_vpot_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -254,6 +254,28 @@ int cpb_vpsi_kpt(cpb_plan* plan, const void* c0, void* c2, long ld, int nstate, 
                  const double* hgkp, const double* hgkm, const double* vpot, int ngroups, int my_group,
                  unsigned flags);
 
+/* ---- Hartree-Fock exchange ----------------------------------------------------------
+ *   cpb_hfx_dev   SUBROUTINE hfx_old(c0,c2,f,psia,nstate,ehfx,vhfx) (hfx_utils.mod.F90:80-965) for func1%mhfx = 1
+ *                 at the Gamma point without LSD and without Wannier / integral screening (hfxc3%twscr =
+ *                 .FALSE.), one task, one group: every occupied state (f >= 1e-6) with itself (hfxaa :1203-1260)
+ *                 and with every other occupied state (hfxab / hfxab2 :1034-1201): pair density psi_a psi_b /
+ *                 omega -> dense forward transform on the PAIR-DENSITY set -> vpotg = -pf scgx rho(G), the pair
+ *                 energy -> dense inverse -> v(r) (psi_a + i psi_b) -> sparse forward transform on the
+ *                 wavefunction set -> c2a, c2b updated.  Two plans on the same mesh and device: `plan` built
+ *                 from the wavefunction sphere (nzfs / inzs), `plan_dens` from the vectors of the pair-density
+ *                 set (nzff / inzf, jhg = its ngw); scgx_dev: the Coulomb kernel of that set (cppt scgx), jhg
+ *                 doubles.  pfl: 0.25 (times func3%phfx for a hybrid functional).  On return c2 += C2_hfx,
+ *                 *ehfx = the exchange energy (:905), *vhfx = sum_i dotp(c0_i, c2_i) of the updated c2 (:907-909).
+ *                 The real-space states stay in HBM for the duration of the call (8 nnr1 bytes per occupied
+ *                 state, the reference's rswfx).  Not covered (the shim takes the original path): LSD, k-points,
+ *                 screening (twscr / twfc), the 2-D task grid over pairs, hfxpsi / hfxrpa. */
+int cpb_hfx_dev(cpb_plan* plan, cpb_plan* plan_dens, const void* c0_dev, void* c2_dev, long ld, int nstate,
+                const double* f, const double* scgx_dev, double pfl, double* ehfx, double* vhfx, unsigned flags,
+                void* stream);
+/* host-pointer form (what the Fortran shim binds): all arrays in host memory, staged per call */
+int cpb_hfx(cpb_plan* plan, cpb_plan* plan_dens, const void* c0, void* c2, long ld, int nstate, const double* f,
+            const double* scgx, double pfl, double* ehfx, double* vhfx, unsigned flags);
+
 /* ---- cross-group collectives over NVLink peer memory ----------------------------------------
  * One process per GPU (the reference's CP_GROUPS layout, one group per MPI rank).  Each rank
  * creates a SEGMENT of device memory, the ranks exchange the 64-byte handles with whatever they

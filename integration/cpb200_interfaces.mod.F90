@@ -24,7 +24,7 @@ MODULE cpb200_interfaces
 
   PUBLIC :: cpb_length_supported, cpb_plan_create, cpb_plan_destroy
   PUBLIC :: cpb_rhoofr, cpb_vpsi, cpb_rhoofr_lsd, cpb_vpsi_lsd, cpb_c0_invalidate
-  PUBLIC :: cpb_rhoofr_kpt, cpb_vpsi_kpt, cpb_tauofr, cpb_vtaupsi, cpb_vofrho_local
+  PUBLIC :: cpb_rhoofr_kpt, cpb_vpsi_kpt, cpb_tauofr, cpb_vtaupsi, cpb_vofrho_local, cpb_hfx
   PUBLIC :: cpb_peer_create, cpb_peer_connect, cpb_peer_local_ptr, cpb_peer_allreduce_f64, &
        cpb_peer_bcast_f64, cpb_peer_check, cpb_peer_destroy, cpb_peer_redist_c2, cpb_peer_allgather_f64, &
        cpb_peer_allreduce_scalars, cpb_peer_set_timeout_ms
@@ -162,6 +162,20 @@ MODULE cpb200_interfaces
        REAL(c_double), INTENT(inout) :: v(*)
        REAL(c_double), INTENT(out) :: ener(9)
      END FUNCTION cpb_vofrho_local
+
+     ! hfx_old(c0,c2,f,psia,nstate,ehfx,vhfx) (hfx_utils.mod.F90:80-965), func1%mhfx = 1, Gamma point, no LSD, no
+     ! screening: plan = wavefunction set, plan_dens = pair-density set (nzff / inzf, jhg vectors), scgx(jhg)
+     INTEGER(c_int) FUNCTION cpb_hfx(plan, plan_dens, c0, c2, ld, nstate, f, scgx, pfl, ehfx, vhfx, flags) &
+          BIND(c, name='cpb_hfx')
+       IMPORT :: c_int, c_long, c_ptr, c_double
+       TYPE(c_ptr), VALUE :: plan, plan_dens
+       TYPE(c_ptr), VALUE :: c0, c2                      ! C_LOC(c0(1,1)), C_LOC(c2(1,1))
+       INTEGER(c_long), VALUE :: ld
+       INTEGER(c_int), VALUE :: nstate, flags
+       REAL(c_double), INTENT(in) :: f(*), scgx(*)
+       REAL(c_double), VALUE :: pfl                      ! 0.25 (x func3%phfx for a hybrid)
+       REAL(c_double), INTENT(out) :: ehfx, vhfx
+     END FUNCTION cpb_hfx
 
      ! cross-group collectives over NVLink peer memory (device-resident runs, one group per GPU)
      INTEGER(c_int) FUNCTION cpb_peer_create(seg, device, rank, world, bytes, handle_out) &

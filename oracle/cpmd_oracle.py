@@ -801,3 +801,93 @@ def synthetic_inputs(geo: Geometry, nstate, seed=None, f_pattern="all2"):
     v = np.zeros((geo.kr[2], geo.kr[1], geo.kr[0]))
     v[:n3, :n2, :n1] = -rng.random((n3, n2, n1))
     return c0, f, v.reshape(-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Hartree-Fock exchange: hfx_old with func1%mhfx = 1, Gamma point, no LSD, no
+# Wannier / integral screening, one task, one group (hfx_utils.mod.F90:80-965)
+# ----------------------------------------------------------------------------------------------
+
+def _psi_real(geo_w: Geometry, c):
+    """psia = 0; set_psi_1_state_g(zone, c, psia); invfftn(psia,.TRUE.) (hfx_utils.mod.F90:490-491): the
+    real-space state on the wavefunction FFT set, box-centre convention (no phasen), padded, complex."""
+    return invfftn_sparse(geo_w, set_psi_1_state_g(geo_w, c))
+
+
+def _hfx_pair(geo_w, geo_d, psia, psib, iran, pf, scgx, omega):
+    """hfxab (hfx_utils.mod.F90:1034-1110): returns (ehfx, dc2a, dc2b) with c2a += dc2a, c2b += dc2b.
+    ``psib`` carries the partner state in its real (iran = 1) or imaginary (iran = 2) part."""
+    b = psib.real if iran == 1 else psib.imag
+    psic = (psia.real * b).astype(np.complex128) / omega                       # :1052-1063
+    g = fwfftn_dense(geo_d, psic)                                              # :1064
+    rg = g[geo_d.nzhs - 1]
+    vpotg = -pf * scgx * rg                                                    # :1068
+    ehfx = float(np.sum(4.0 * vpotg * np.conj(rg)).real)                       # :1069
+    if geo_d.geq0:
+        ehfx -= float((2.0 * vpotg[0] * np.conj(rg[0])).real)                  # :1071
+    vpotr = g_to_r(geo_d, vpotg).real                                          # :1072-1084
+    psic = vpotr * (psia.real + 1j * b)                                        # :1085-1095
+    r = fwfftn_sparse(geo_w, psic)                                             # :1096
+    fp = r[geo_w.nzhs - 1] + r[geo_w.indzs - 1]
+    fm = r[geo_w.nzhs - 1] - r[geo_w.indzs - 1]
+    dc2b = -(fp.real + 1j * fm.imag)                                           # :1103
+    dc2a = -(fp.imag - 1j * fm.real)                                           # :1104
+    return ehfx, dc2a, dc2b
+
+
+def _hfx_diag(geo_w, geo_d, psia, pf, scgx, omega):
+    """hfxaa (hfx_utils.mod.F90:1203-1260): returns (ehfx, dc2a)."""
+    psic = (psia.real * psia.real).astype(np.complex128) / omega               # :1218-1222
+    g = fwfftn_dense(geo_d, psic)
+    rg = g[geo_d.nzhs - 1]
+    vpotg = -pf * scgx * rg                                                    # :1228
+    ehfx = float(np.sum(2.0 * vpotg * np.conj(rg)).real)                       # :1229
+    if geo_d.geq0:
+        ehfx -= float((vpotg[0] * np.conj(rg[0])).real)                        # :1231
+    vpotr = g_to_r(geo_d, vpotg).real
+    r = fwfftn_sparse(geo_w, vpotr * psia.real.astype(np.complex128))          # :1245-1249
+    fp = r[geo_w.nzhs - 1] + r[geo_w.indzs - 1]
+    fm = r[geo_w.nzhs - 1] - r[geo_w.indzs - 1]
+    return ehfx, -(fp.real + 1j * fm.imag)                                     # :1256
+
+
+def hfx(geo_w: Geometry, geo_d: Geometry, c0, c2, f, scgx, omega, pfl=0.25):
+    """``hfx_old(c0,c2,f,psia,nstate,ehfx,vhfx)`` (hfx_utils.mod.F90:80-965) for func1%mhfx = 1, Gamma point,
+    cntl%tlsd = .FALSE. (pfl = 0.25, times func3%phfx for a hybrid: pass it in ``pfl``), hfxc3%twscr =
+    .FALSE., one task and one group: every occupied state ia (f >= 1e-6, :474) gets its diagonal term hfxaa
+    with pfx = pfl f(ia)^2 (:497-502) and every unordered pair (ia, ib) of occupied states one hfxab with pfx
+    = pfl f(ia) f(ib) (:709-752; part_1d_symm_holds_pair picks one of the two orders - the result does not
+    depend on which, nor on the packing of two partners into one transform, hfxab2).  ``geo_w``: the
+    wavefunction FFT set (nzfs/inzs), ``geo_d``: the set of the pair densities (nzff/inzf, jhg = geo_d.ngw
+    vectors) with the Coulomb kernel ``scgx``.  Returns (c2_new, ehfx, vhfx): c2 += C2_hfx (:819), ehfx =
+    omega * sum (:905), vhfx = sum_ia dotp(c0_ia, c2_new_ia) (:907-909)."""
+    nstate = c0.shape[0]
+    occ = [i for i in range(nstate) if f[i] >= 1.0e-6]
+    psi = {i: _psi_real(geo_w, c0[i, :geo_w.ngw]) for i in occ}
+    c2_hfx = np.zeros((nstate, geo_w.ngw), dtype=np.complex128)
+    ehfx = 0.0
+    for ia in occ:
+        e, d = _hfx_diag(geo_w, geo_d, psi[ia], pfl * f[ia] * f[ia], scgx, omega)
+        ehfx += e
+        c2_hfx[ia] += d
+        for ib in occ:
+            if ib <= ia:
+                continue
+            e, da, db = _hfx_pair(geo_w, geo_d, psi[ia], psi[ib], 1, pfl * f[ia] * f[ib], scgx, omega)
+            ehfx += e
+            c2_hfx[ia] += da
+            c2_hfx[ib] += db
+    out = np.array(c2, dtype=np.complex128, copy=True)
+    out[:, :geo_w.ngw] += c2_hfx
+    ehfx *= omega
+    vhfx = sum(dotp(geo_w, c0[i, :geo_w.ngw], out[i, :geo_w.ngw]) for i in range(nstate))
+    return out, ehfx, vhfx
+
+
+def hfx_coulomb_kernel(geo_d: Geometry, tpiba2):
+    """A Coulomb kernel for synthetic HFX inputs: scgx = 4 pi / (tpiba2 hg), 0 at G = 0 (the reference
+    builds scgx in hfx_drivers / cppt with its own G = 0 treatment; the library takes it as an input)."""
+    s = np.zeros(geo_d.ngw)
+    nz = geo_d.hg > 1.0e-12
+    s[nz] = 4.0 * np.pi / (tpiba2 * geo_d.hg[nz])
+    return s

@@ -688,3 +688,47 @@ def test_charge_check_flag(emu_cdll):
     assert ei.value.code == lib.CPB_ERR_CHARGE
     _, _, rg, rr = p.rhoofr(bad, d["f"])
     assert abs(rg - rr) > 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# Hartree-Fock exchange
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nr,ns", [(16, 5), ((16, 20, 24), 4), (24, 3)])
+def test_hfx_matches_oracle(emu_cdll, nr, ns):
+    gw = orc.make_geometry(nr)
+    gd = orc.make_density_geometry(nr)
+    tp, om = 0.9, 1.3
+    c0, f, _ = orc.synthetic_inputs(gw, ns, f_pattern="mixed")
+    scgx = orc.hfx_coulomb_kernel(gd, tp)
+    pw = Plan(gw.nr, gw.inyh, gw.hg, tp, om, max_batch=2, _cdll=emu_cdll)
+    pd = Plan(gd.nr, gd.inyh, gd.hg, tp, om, max_batch=1, _cdll=emu_cdll)
+    c2 = 0.25 * c0
+    want, e_ref, v_ref = orc.hfx(gw, gd, c0, c2, f, scgx, om)
+    e, v = pw.hfx_dev(pd, c0, c2, f, scgx)
+    assert relmax(c2, want) < RTOL
+    assert abs(e - e_ref) < ETOL * max(1.0, abs(e_ref)) and abs(v - v_ref) < ETOL * max(1.0, abs(v_ref))
+    # the exchange energy is the Euler sum of its own gradient: sum_i dotp(c0_i, dC2_i) = -2 ehfx
+    z = np.zeros_like(c0)
+    e2, v2 = pw.hfx_dev(pd, c0, z, f, scgx)
+    assert abs(v2 + 2.0 * e2) < 1e-10 * abs(e2) and abs(e2 - e) < 1e-12 * abs(e)
+    # hybrid prefactor
+    z2 = np.zeros_like(c0)
+    e3, _ = pw.hfx_dev(pd, c0, z2, f, scgx, pfl=0.25 * 0.2)
+    assert abs(e3 - 0.2 * e) < 1e-12 * abs(e) and relmax(z2, 0.2 * z) < 1e-13
+
+
+def test_hfx_host_form(emu_cdll):
+    gw = orc.make_geometry(16)
+    gd = orc.make_density_geometry(16)
+    c0, f, _ = orc.synthetic_inputs(gw, 4)
+    scgx = orc.hfx_coulomb_kernel(gd, 1.0)
+    pw = Plan(gw.nr, gw.inyh, gw.hg, max_batch=2, _cdll=emu_cdll)
+    pd = Plan(gd.nr, gd.inyh, gd.hg, max_batch=1, _cdll=emu_cdll)
+    ld = gw.ngw + 3
+    c0p = np.zeros((4, ld), complex)
+    c0p[:, :gw.ngw] = c0
+    c2 = np.full((4, ld), 1.0 - 2.0j)
+    want, e_ref, _ = orc.hfx(gw, gd, c0, c2[:, :gw.ngw], f, scgx, 1.0)
+    e, v = pw.hfx(pd, c0p, c2, f, scgx)
+    assert relmax(c2[:, :gw.ngw], want) < RTOL and abs(e - e_ref) < ETOL * abs(e_ref)
+    assert np.all(c2[:, gw.ngw:] == 1.0 - 2.0j)

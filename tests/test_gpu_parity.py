@@ -670,3 +670,42 @@ def test_c0_upload_and_charge_check(dev):
     assert ei.value.code == lib.CPB_ERR_CHARGE and "DENSITY SUMS" in str(ei.value)
     _, _, rg_p, rr_p = plan.rhoofr(poisoned, d["f"])           # without the flag: sums returned, no error
     assert abs(rg_p - rr_p) > 1e-6
+
+
+@pytest.mark.parametrize("nr,ns", [(16, 5), ((16, 20, 24), 4), (48, 6), (96, 5)])
+def test_hfx_device_matches_oracle(dev, nr, ns):
+    """cpb_hfx_dev (hfx_old, Gamma point, no LSD, no screening: hfx_utils.mod.F90:80-965) against the oracle."""
+    gw = orc.make_geometry(nr)
+    gd = orc.make_density_geometry(nr)
+    tp, om = 0.9, 1.3
+    c0, f, _ = orc.synthetic_inputs(gw, ns, f_pattern="mixed")
+    scgx = orc.hfx_coulomb_kernel(gd, tp)
+    pw = Plan(gw.nr, gw.inyh, gw.hg, tp, om, max_batch=2)
+    pdn = Plan(gd.nr, gd.inyh, gd.hg, tp, om, max_batch=1)
+    c2_h = 0.25 * c0
+    want, e_ref, v_ref = orc.hfx(gw, gd, c0, c2_h, f, scgx, om)
+    c0d = torch.from_numpy(c0).to(dev)
+    c2 = torch.from_numpy(c2_h).to(dev)
+    e, v = pw.hfx_dev(pdn, c0d, c2, f, torch.from_numpy(scgx).to(dev))
+    assert relmax(c2.cpu().numpy(), want) < RTOL
+    assert abs(e - e_ref) < ETOL * max(1.0, abs(e_ref)) and abs(v - v_ref) < ETOL * max(1.0, abs(v_ref))
+
+
+def test_hfx_full_size_identities(dev):
+    """192^3, 6 states: Euler identity sum_i dotp(c0_i, dC2_i) = -2 ehfx and bit-stable repeat."""
+    n, ns = 192, 6
+    d = synthetic.make_inputs(n, ns)
+    from cpmd_b200 import gvec
+    inyh_d, hg_d = gvec.half_sphere((n, n, n), (n / 2.0) ** 2)
+    pw = Plan(d["nr"], d["inyh"], d["hg"], max_batch=4)
+    pdn = Plan((n, n, n), inyh_d, hg_d, max_batch=1)
+    scgx = np.zeros(hg_d.shape[0])
+    scgx[1:] = 4.0 * np.pi / hg_d[1:]
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    sc = torch.from_numpy(scgx).to(dev)
+    z = torch.zeros_like(c0)
+    e, v = pw.hfx_dev(pdn, c0, z, d["f"], sc)
+    assert e < 0.0 and abs(v + 2.0 * e) < 1e-10 * abs(e)
+    z2 = torch.zeros_like(c0)
+    e2, v2 = pw.hfx_dev(pdn, c0, z2, d["f"], sc)
+    assert (e2, v2) == (e, v) and torch.equal(z, z2)

@@ -440,3 +440,36 @@ def test_pocketfft_staged_restatement_matches_dense(nr, ns):
         c2a = orc.vpsi(geo, c0, 0.5 * c0, f, v, 0.9, g, ng)
         c2b = spf.vpsi(geo, c0, 0.5 * c0, f, v, 0.9, g, ng, batch=3)
         assert np.abs(c2a - c2b).max() <= 1e-13 * np.abs(c2a).max()
+
+
+def test_hfx_known_answers():
+    """Hartree-Fock exchange restatement (hfx_utils.mod.F90:80-965, 1034-1260) against closed forms.
+    One state, one plane wave c(G1) = 1/sqrt(2): psi(r) = +-sqrt(2) cos(G1 r), pair density psi^2 / omega =
+    (1 + cos(2 G1 r)) / omega, i.e. rho(0) = 1/omega, rho(+-2 G1) = 1/(2 omega); with pf = pfl f^2
+    ehfx = -omega pf [scgx(0) rho(0)^2 + 2 scgx(2 G1) rho(2 G1)^2] (hfxaa :1226-1231, times omega :905).
+    Then: Euler identity sum_i dotp(c0_i, dC2_i) = -2 ehfx, degree-4 homogeneity, invariance under the order of
+    the states, and additivity - unoccupied states (f < 1e-6) take no part (:474)."""
+    nr = 16
+    gw = orc.make_geometry(nr)
+    gd = orc.make_density_geometry(nr)
+    om, tp, fa = 1.7, 0.8, 2.0
+    scgx = orc.hfx_coulomb_kernel(gd, tp) + 0.3          # a non-zero G = 0 entry exercises its special weight
+    ig1 = int(np.nonzero((gw.inyh[0] - 9 == 1) & (gw.inyh[1] - 9 == 2) & (gw.inyh[2] - 9 == 0))[0][0])
+    c0 = np.zeros((1, gw.ngw), complex)
+    c0[0, ig1] = 1.0 / np.sqrt(2.0)
+    out, e, v = orc.hfx(gw, gd, c0, np.zeros_like(c0), np.array([fa]), scgx, om)
+    g2 = 2 * (gw.inyh[:, ig1] - 9)
+    j = int(np.nonzero(np.all(gd.inyh - 9 == g2[:, None], axis=0) | np.all(gd.inyh - 9 == -g2[:, None], axis=0))[0][0])
+    pf = 0.25 * fa * fa
+    want = -om * pf * (scgx[0] / om ** 2 + 2.0 * scgx[j] * (0.5 / om) ** 2)
+    assert abs(e - want) < 1e-13 * abs(want)
+    assert abs(v + 2.0 * e) < 1e-12 * abs(e)
+    c0, f, _ = orc.synthetic_inputs(gw, 5, f_pattern="mixed")
+    z = np.zeros_like(c0)
+    o1, e1, v1 = orc.hfx(gw, gd, c0, z, f, scgx, om)
+    assert abs(v1 + 2.0 * e1) < 1e-11 * abs(e1)
+    o2, e2, _ = orc.hfx(gw, gd, 1.5 * c0, z, f, scgx, om)
+    assert abs(e2 - 1.5 ** 4 * e1) < 1e-11 * abs(e2) and np.abs(o2 - 1.5 ** 3 * o1).max() < 1e-11 * np.abs(o2).max()
+    keep = f >= 1e-6
+    o3, e3, _ = orc.hfx(gw, gd, c0[keep], z[keep], f[keep], scgx, om)
+    assert abs(e3 - e1) < 1e-12 * abs(e1) and np.abs(o3 - o1[keep]).max() < 1e-13 and not o1[~keep].any()
