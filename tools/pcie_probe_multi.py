@@ -75,7 +75,7 @@ if rank == 0:
 for name, up, down in (("H2D", True, False), ("D2H", False, True), ("duplex", True, True)):
     run(up, down, reps=2)
     solo = [run(up, down, solo_rank=r) for r in range(world)]
-    solo = [max(g) for g in zip(*[gather(s) for s in solo])] if world > 1 else solo
+    solo = [max(gather(s)) for s in solo]
     together = gather(run(up, down))
     if rank == 0:
         print(f"{name:7s} {mb} MB buffers: alone per rank " + " ".join(f"{g:5.1f}" for g in solo) +
