@@ -3,6 +3,7 @@
 // them.  The x, y and z launchers of a plan may come from three different lengths.
 #pragma once
 #include "kernels.h"
+#include "kernels_zw.h"
 
 namespace cpb {
 
@@ -42,6 +43,16 @@ struct AxisKernels {
                 int xt0, int nxc, bool half);
   void (*z_vpsi)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
                  int ppg, bool half);
+  // warp-autonomous z passes (kernels_zw.h); null if the length has no CPB_ZW factorisation.  Band-pruned
+  // only: usable when the z band lies inside [zw_rb*zw_klo, zw_rb*zw_khi)
+  void (*z_rho_w)(cudaStream_t, const cplx* T2, double* rho, const PlanDev&, const PairDev&, int npair,
+                  int xt0, int nxc);
+  void (*z_vpsi_w)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
+                   int ppg);
+  int zw_ra, zw_rb, zw_klo, zw_khi;
+  int zw_units_per_row;   // warps (column groups) per 128-byte row of a tile
+  int zw_warps;           // warps per block
+  int zw_blocks_per_sm;   // occupancy the warp kernels are compiled for
   // dense transforms (real fields on the density-cutoff sphere): z passes with phasen
   void (*z_fwd_real)(cudaStream_t, const double* fre, const double* fim, cplx* T2, const PlanDev&, int xt0, int nxc,
                      bool half, const double* mul, double scale);

@@ -189,6 +189,37 @@ void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, in
   else z_vpsi_t<false>(st, T2, vpot, pd, npair, xt0, nxc, ppg);
 }
 
+// warp-autonomous z passes (kernels_zw.h), band-pruned instantiation only
+using ZP = ZWPick<N>;
+constexpr bool kHasZW = ZP::ra != 0;
+template <bool HAS, int DUMMY = 0>
+struct ZWLaunch {
+  static constexpr void (*rho)(cudaStream_t, const cplx*, double*, const PlanDev&, const PairDev&, int, int, int) = nullptr;
+  static constexpr void (*vpsi)(cudaStream_t, cplx*, const double*, const PlanDev&, int, int, int, int) = nullptr;
+  static constexpr int ra = 0, rb = 0, klo = 0, khi = 0, upr = 0, warps = 0, minb = 0;
+};
+template <int DUMMY>
+struct ZWLaunch<true, DUMMY> {  // partial specialisation: members are only instantiated where used
+  static constexpr int ra = ZP::ra ? ZP::ra : 4, rb = ZP::rb ? ZP::rb : 4, L = ZP::l ? ZP::l : 4;
+  using C = ZWCfg<ra, rb, L, true>;
+  static constexpr int klo = C::KR::lo, khi = C::KR::hi, upr = B / C::CW, warps = C::WARPS, minb = C::MINB;
+  static int grid_y(const PlanDev& pd) { return (pd.n2 * upr + warps - 1) / warps; }
+  static void rho(cudaStream_t st, const cplx* T2, double* rho_, const PlanDev& pd, const PairDev& pr, int npair,
+                  int xt0, int nxc) {
+    auto k = k_zw_rho<ra, rb, L, B, true>;
+    allow_smem(k, C::SMEM);
+    CPB_LAUNCH(k, dim3(nxc, grid_y(pd)), dim3(C::NT), C::SMEM, st, T2, rho_, pd, pr, npair, xt0);
+  }
+  static void vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
+                   int ppg) {
+    auto k = k_zw_vpsi<ra, rb, L, B, true>;
+    allow_smem(k, C::SMEM);
+    CPB_LAUNCH(k, dim3(nxc, grid_y(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM, st, T2, vpot, pd, xt0, npair,
+               ppg);
+  }
+};
+using ZWL = ZWLaunch<kHasZW>;
+
 template <bool HALF>
 void z_fwd_real_t(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0,
                   int nxc, const double* mul, double scale) {
@@ -216,7 +247,9 @@ void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const
 }
 
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
-                            x_inv, x_inv_gk, x_fwd, x_inv_m, x_fwd_m, y_inv, y_fwd, z_rho, z_vpsi, z_fwd_real, z_inv_real,
+                            x_inv, x_inv_gk, x_fwd, x_inv_m, x_fwd_m, y_inv, y_fwd, z_rho, z_vpsi,
+                            ZWL::rho, ZWL::vpsi, ZWL::ra, ZWL::rb, ZWL::klo, ZWL::khi, ZWL::upr, ZWL::warps, ZWL::minb,
+                            z_fwd_real, z_inv_real,
                             YZBlocks<R1, R2>::v, XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD,
                             XMCfg<R1, R2, SL, true>::MINB_INV, XMCfg<R1, R2, SL, true>::MINB_FWD};
 

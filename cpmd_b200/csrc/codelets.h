@@ -246,4 +246,66 @@ CPB_HD void dft_in(cplx (&v)[R]) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming forms of the band-pruned transforms, R = D * M (used by the warp-autonomous z kernels,
+// kernels_zw.h).  They touch the R-point transform in D groups of M, so that only the band elements
+// and one M-point working set are live in registers at a time.
+//
+// dft_in_dif: decimation in frequency over the output index p = D*m + r.  v[k] is non-zero only for
+// k in [LO, HI).   g_r[u] = sum_c v[u + M c] w_R^((u + M c) r),   Y[D m + r] = DFT_M(g_r)[m];
+// emit(IC<p>, Y[p]) is called group by group (r = 0 .. D-1), so the caller can twiddle and store a
+// group before the next one is computed.
+// ---------------------------------------------------------------------------------------------
+template <int R, int D, bool INV, int LO, int HI, class E>
+CPB_HD void dft_in_dif(const cplx (&v)[R], E&& emit) {
+  static_assert(R % D == 0, "R = D * M");
+  constexpr int M = R / D;
+  static_for<0, D>([&](auto rr) {
+    constexpr int r = decltype(rr)::value;
+    cplx g[M];
+    static_for<0, M>([&](auto uu) {
+      constexpr int u = decltype(uu)::value;
+      bool first = true;  // folded at compile time (every branch below is constexpr)
+      g[u] = mk(0.0, 0.0);
+      static_for<0, D>([&](auto cc) {
+        constexpr int k = u + M * decltype(cc)::value;
+        if constexpr (k >= LO && k < HI) {
+          const cplx t = mul_root<R, k * r, INV>(v[k]);
+          g[u] = first ? t : cadd(g[u], t);
+          first = false;
+        }
+      });
+    });
+    dft<M, INV>(g);
+    static_for<0, M>([&](auto mm) {
+      constexpr int m = decltype(mm)::value;
+      emit(IC<D * m + r>{}, g[m]);
+    });
+  });
+}
+
+// dft_out_dit: decimation in time over the input index p = D*m + r, only the outputs t in [LO, HI)
+// are produced (the others of z are left untouched).  in(IC<p>) returns input p.
+//   E_r = DFT_M(in(D m + r)),   Z[t] = sum_r w_R^(r t) E_r[t mod M]
+template <int R, int D, bool INV, int LO, int HI, class IN>
+CPB_HD void dft_out_dit(IN&& in, cplx (&z)[R]) {
+  static_assert(R % D == 0, "R = D * M");
+  constexpr int M = R / D;
+  static_for<0, D>([&](auto rr) {
+    constexpr int r = decltype(rr)::value;
+    cplx e[M];
+    static_for<0, M>([&](auto mm) {
+      constexpr int m = decltype(mm)::value;
+      e[m] = in(IC<D * m + r>{});
+    });
+    dft<M, INV>(e);
+    static_for<LO, HI>([&](auto tt) {
+      constexpr int t = decltype(tt)::value;
+      const cplx c = mul_root<R, r * t, INV>(e[t % M]);
+      if constexpr (r == 0) z[t] = c;
+      else z[t] = cadd(z[t], c);
+    });
+  });
+}
+
 }  // namespace cpb

@@ -112,6 +112,7 @@ struct cpb_plan {
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
+  bool zw = false;  // z passes of the wavefunction path run the warp-autonomous kernels (kernels_zw.h)
   bool mirror = false;        // mirror-pair x kernels usable (ray numbering mirror-symmetric; CPB_X_MIRROR=0 disables)
   int nbx_m = 0;              // their blocks per pair group
   double* d_kinpart = nullptr;  // kin_energy / dotp block partials of k_x_inv_m, [pair][nbx_m][4]
@@ -544,6 +545,22 @@ bool psi_reserve(cpb_plan* p, int npairs) {
   return true;
 }
 
+// z passes of the wavefunction path: warp-autonomous kernels where the plan can use them
+void launch_z_rho(cpb_plan* p, cudaStream_t st, const cplx* T2, double* rho, const PairDev& pr, int nb, int xt0, int nxc) {
+  if (p->zw) p->kz->z_rho_w(st, T2, rho, p->pd, pr, nb, xt0, nxc);
+  else p->kz->z_rho(st, T2, rho, p->pd, pr, nb, xt0, nxc, p->half_z);
+}
+void launch_z_vpsi(cpb_plan* p, cudaStream_t st, cplx* T2, const double* vpot, int nb, int xt0, int nxc) {
+  if (p->zw) {
+    const AxisKernels* k = p->kz;
+    const int gy = (p->nr[1] * k->zw_units_per_row + k->zw_warps - 1) / k->zw_warps;
+    p->kz->z_vpsi_w(st, T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * gy, k->zw_blocks_per_sm));
+  } else {
+    p->kz->z_vpsi(st, T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm),
+                  p->half_z);
+  }
+}
+
 // batches never straddle the channel boundary: [0, n0) work on channel 0, [n0, np) on channel 1
 struct BatchSpan {
   int off, n, chan;
@@ -575,7 +592,7 @@ void run_rhoofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
       { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
       // rho is read-modify-written batch after batch: keep the order of the single-stream run
       if (b > 0 && p->nws > 1) rt::stream_wait(w.s, p->ws[(b - 1) % p->nws].ev_rho);
-      { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, T2, rho, p->pd, prb, nb, xt0, nxc, p->half_z); }
+      { Timed t(p, w.s, CPB_K_Z_RHO); launch_z_rho(p, w.s, T2, rho, prb, nb, xt0, nxc); }
       rt::event_record(w.ev_rho, w.s);
     }
     if (hooks) hooks->after_batch(b, off, nb, w.s);
@@ -607,7 +624,7 @@ void run_vpsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev& pr
       cplx* T2 = reuse ? reuse + (size_t)off * p->t2_pair : w.T2;
       if (!reuse) { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
       if (vready && b < p->nws && xt0 == 0) rt::stream_wait(w.s, vready);  // first z pass of every work-space stream
-      { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, T2, vpot, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
+      { Timed t(p, w.s, CPB_K_Z_VPSI); launch_z_vpsi(p, w.s, T2, vpot, nb, xt0, nxc); }
       { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
     }
     run_x_fwd(p, w, c0, c2, ldc, prb, nb, accumulate);
@@ -882,6 +899,11 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
       if (const char* e = std::getenv("CPB_NO_HALF")) {
         if (std::atoi(e)) p->half_x = p->half_y = p->half_z = false;
       }
+      // warp-autonomous z kernels: band-pruned instantiation only, own factorisation of n3
+      p->zw = p->half_z && p->kz->z_rho_w && zlo >= p->kz->zw_rb * p->kz->zw_klo && zhi < p->kz->zw_rb * p->kz->zw_khi;
+      if (const char* e = std::getenv("CPB_ZW")) {
+        if (!std::atoi(e)) p->zw = false;
+      }
     }
     {
       // mirror-pair x kernels: the mirror of internal ray r must be ray nrays - 1 - r (true whenever the ray
@@ -1041,6 +1063,9 @@ int cpb_plan_get_info(const cpb_plan* p, cpb_plan_info* info) {
   info->band_pruned[2] = p->half_z;
   info->chunk_xtiles = p->chunk_xt;
   info->streams = p->nws;
+  info->z_warp_kernels = p->zw ? 1 : 0;
+  info->z_warp_radix[0] = p->zw ? p->kz->zw_ra : 0;
+  info->z_warp_radix[1] = p->zw ? p->kz->zw_rb : 0;
   return CPB_OK;
 }
 
@@ -1552,7 +1577,7 @@ void run_tauofr(cpb_plan* p, const cplx* c0, long ldc, const PairDev& pr, int np
         const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
         { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm), p->half_y); }
         if (b > 0 && p->nws > 1 && dir == 0) rt::stream_wait(w.s, p->ws[(b - 1) % p->nws].ev_rho);
-        { Timed t(p, w.s, CPB_K_Z_RHO); p->kz->z_rho(w.s, w.T2, tau, p->pd, prb, nb, xt0, nxc, p->half_z); }
+        { Timed t(p, w.s, CPB_K_Z_RHO); launch_z_rho(p, w.s, w.T2, tau, prb, nb, xt0, nxc); }
       }
     }
     rt::event_record(w.ev_rho, w.s);
@@ -1577,7 +1602,7 @@ void run_vtaupsi(cpb_plan* p, const cplx* c0, cplx* c2, long ldc, const PairDev&
         const int nxc = std::min(p->chunk_xt, p->nxt - xt0);
         const int ppg_y = pairs_per_group(p, nb, nxc * p->nzb, p->ky->yz_blocks_per_sm);
         { Timed t(p, w.s, CPB_K_Y_INV); p->ky->y_inv(w.s, w.T1, w.T2, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
-        { Timed t(p, w.s, CPB_K_Z_VPSI); p->kz->z_vpsi(w.s, w.T2, vtau, p->pd, nb, xt0, nxc, pairs_per_group(p, nb, nxc * p->nr[1], p->kz->yz_blocks_per_sm), p->half_z); }
+        { Timed t(p, w.s, CPB_K_Z_VPSI); launch_z_vpsi(p, w.s, w.T2, vtau, nb, xt0, nxc); }
         { Timed t(p, w.s, CPB_K_Y_FWD); p->ky->y_fwd(w.s, w.T2, w.T1, p->pd, nb, xt0, nxc, ppg_y, p->half_y); }
       }
       for (int o = 0; o < nb; o += p->x_sub) {

@@ -47,6 +47,8 @@ class PlanInfo(C.Structure):
         ("band_pruned", C.c_int * 3),
         ("chunk_xtiles", C.c_int),
         ("streams", C.c_int),
+        ("z_warp_kernels", C.c_int),
+        ("z_warp_radix", C.c_int * 2),
     ]
 
 

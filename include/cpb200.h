@@ -92,6 +92,8 @@ typedef struct {
   int band_pruned[3]; /* 1: the axis runs the band-pruned kernel variants (coefficients in the middle half) */
   int chunk_xtiles;   /* x tiles (of 8 columns) per y/z chunk (default: all of them, one y and one z launch per batch) */
   int streams;        /* work spaces / streams the batches of a call alternate between */
+  int z_warp_kernels; /* 1: the z passes of rhoofr / vpsi run the warp-autonomous kernels (kernels_zw.h) */
+  int z_warp_radix[2];/* their factorisation of n3 (band-side radix, real-space-side radix), 0 if unused */
 } cpb_plan_info;
 
 const char* cpb_last_error(void);

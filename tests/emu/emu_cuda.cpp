@@ -19,6 +19,7 @@ struct Fiber {
   ucontext_t ctx;
   std::unique_ptr<char[]> stack;
   bool done = false;
+  int wait = 0;  // 0: runnable, 1: at __syncthreads, 2: at __syncwarp
 };
 
 struct BlockState {
@@ -47,33 +48,63 @@ static void run_block(BlockState& bs, dim3 block) {
   for (unsigned t = 0; t < nt; ++t) {
     Fiber& f = bs.fibers[t];
     f.done = false;
+    f.wait = 0;
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack.get();
     f.ctx.uc_stack.ss_size = kStack;
     f.ctx.uc_link = &bs.sched;
     makecontext(&f.ctx, (void (*)())trampoline, 0);
   }
-  bool any = true;
-  while (any) {
-    any = false;
-    unsigned ndone = 0;
+  for (;;) {
+    // run every runnable fiber until it waits at a barrier or exits
     for (unsigned t = 0; t < nt; ++t) {
       Fiber& f = bs.fibers[t];
-      if (f.done) {
-        ++ndone;
-        continue;
-      }
+      if (f.done || f.wait != 0) continue;
       threadIdx.x = t % block.x;
       threadIdx.y = (t / block.x) % block.y;
       threadIdx.z = t / (block.x * block.y);
       bs.current = &f;
       swapcontext(&bs.sched, &f.ctx);
-      if (!f.done) any = true; else ++ndone;
     }
-    if (any && ndone != 0) {
+    // warp barriers: a warp whose live fibers all wait at __syncwarp goes on
+    bool released = false;
+    for (unsigned w0 = 0; w0 < nt; w0 += 32) {
+      const unsigned w1 = w0 + 32 < nt ? w0 + 32 : nt;
+      unsigned live = 0, atwarp = 0;
+      for (unsigned t = w0; t < w1; ++t) {
+        if (bs.fibers[t].done) continue;
+        ++live;
+        if (bs.fibers[t].wait == 2) ++atwarp;
+      }
+      if (live != 0 && atwarp == live) {
+        for (unsigned t = w0; t < w1; ++t) bs.fibers[t].wait = 0;
+        released = true;
+      } else if (atwarp != 0) {
+        for (unsigned t = w0; t < w1; ++t)
+          if (!bs.fibers[t].done && bs.fibers[t].wait == 0) {
+            std::fprintf(stderr, "emu: inconsistent fiber state at __syncwarp\n");
+            std::abort();
+          }
+      }
+    }
+    if (released) continue;
+    // block barrier: every fiber of the block waits at __syncthreads
+    unsigned ndone = 0, atblock = 0, atwarp = 0;
+    for (unsigned t = 0; t < nt; ++t) {
+      if (bs.fibers[t].done) ++ndone;
+      else if (bs.fibers[t].wait == 1) ++atblock;
+      else ++atwarp;
+    }
+    if (ndone == nt) break;
+    if (atwarp != 0) {
+      std::fprintf(stderr, "emu: deadlock (part of a warp waits at __syncwarp, the rest at __syncthreads or gone)\n");
+      std::abort();
+    }
+    if (ndone != 0) {
       std::fprintf(stderr, "emu: divergent __syncthreads (some threads exited, others wait)\n");
       std::abort();
     }
+    for (unsigned t = 0; t < nt; ++t) bs.fibers[t].wait = 0;
   }
 }
 
@@ -106,5 +137,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 
 void __syncthreads() {
   emu::BlockState* bs = emu::g_bs;
+  bs->current->wait = 1;
+  swapcontext(&bs->current->ctx, &bs->sched);
+}
+
+void __syncwarp() {
+  emu::BlockState* bs = emu::g_bs;
+  bs->current->wait = 2;
   swapcontext(&bs->current->ctx, &bs->sched);
 }

@@ -44,6 +44,7 @@ extern thread_local dim3 blockDim;
 extern thread_local dim3 gridDim;
 
 void __syncthreads();
+void __syncwarp();  // barrier over the (up to) 32 fibers of a warp that have not exited
 
 template <class T>
 static inline T __ldg(const T* p) {

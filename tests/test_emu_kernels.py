@@ -16,7 +16,8 @@ def _plan(d, cdll, **kw):
 
 @pytest.mark.parametrize("n,nstate,mb,fp", [(16, 4, 16, "all2"), (20, 5, 2, "mixed"), (24, 7, 2, "mixed"),
                                             (30, 6, 1, "mixed"), (36, 3, 16, "all2"), (40, 2, 16, "all2"),
-                                            (48, 4, 3, "all2"), (60, 2, 16, "all2")])
+                                            (48, 4, 3, "all2"), (60, 2, 16, "all2"), (32, 5, 3, "mixed"),
+                                            (64, 3, 2, "mixed")])
 def test_kernels_match_oracle(emu_cdll, n, nstate, mb, fp):
     d = synthetic.make_inputs(n, nstate, f_pattern=fp)
     geo = orc.make_geometry(n)
@@ -36,6 +37,33 @@ def test_kernels_match_oracle(emu_cdll, n, nstate, mb, fp):
     # pads of rho are exactly zero
     r3 = rho.reshape(p.kr[2], p.kr[1], p.kr[0])
     assert not r3[n:].any() and not r3[:, n:].any() and not r3[:, :, n:].any()
+
+
+@pytest.mark.parametrize("n,radix", [(16, (4, 4)), (32, (8, 4)), (48, (12, 4)), (64, (8, 8))])
+def test_warp_z_kernels_selected_and_match_block_kernels(emu_cdll, monkeypatch, n, radix):
+    """The warp-autonomous z kernels (kernels_zw.h) are the default where the length has a CPB_ZW
+    factorisation and the band fits; CPB_ZW=0 falls back to the block kernels, same results (both are
+    compared with the oracle in test_kernels_match_oracle; here with each other, incl. odd state counts,
+    several batches and a pair group split)."""
+    d = synthetic.make_inputs(n, 5, f_pattern="mixed")
+    p = _plan(d, emu_cdll, max_batch=2)
+    assert p.info["z_warp_kernels"] and p.info["z_warp_radix"] == radix
+    monkeypatch.setenv("CPB_ZW", "0")
+    q = _plan(d, emu_cdll, max_batch=2)
+    monkeypatch.delenv("CPB_ZW")
+    assert not q.info["z_warp_kernels"] and q.info["z_warp_radix"] == (0, 0)
+    rho_w, ekin_w, *_ = p.rhoofr(d["c0"], d["f"])
+    rho_b, ekin_b, *_ = q.rhoofr(d["c0"], d["f"])
+    assert relmax(rho_w, rho_b) < 1e-13 and abs(ekin_w - ekin_b) < ETOL
+    c2w, c2b = 0.5 * d["c0"], 0.5 * d["c0"]
+    p.vpsi(d["c0"], c2w, d["f"], d["vpot"])
+    q.vpsi(d["c0"], c2b, d["f"], d["vpot"])
+    assert relmax(c2w, c2b) < 1e-13
+
+
+def test_warp_z_kernels_not_used_without_factorisation(emu_cdll):
+    d = synthetic.make_inputs(20, 2)
+    assert not _plan(d, emu_cdll).info["z_warp_kernels"]
 
 
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
