@@ -900,10 +900,11 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
         if (std::atoi(e)) p->half_x = p->half_y = p->half_z = false;
       }
       // warp-autonomous z kernels: band-pruned instantiation only, own factorisation of n3
-      p->zw = p->half_z && p->kz->z_rho_w && zlo >= p->kz->zw_rb * p->kz->zw_klo && zhi < p->kz->zw_rb * p->kz->zw_khi;
-      if (const char* e = std::getenv("CPB_ZW")) {
-        if (!std::atoi(e)) p->zw = false;
-      }
+      // (opt-in with CPB_ZW=1 while they are slower than the block kernels on the 192^3 case: 2.13 vs 1.99 ms
+      // z_rho, 4.17 vs 3.53 ms z_vpsi per 128 pairs, profiles/r02k_full_zw_192x128.txt)
+      const bool zw_ok = p->half_z && p->kz->z_rho_w && zlo >= p->kz->zw_rb * p->kz->zw_klo && zhi < p->kz->zw_rb * p->kz->zw_khi;
+      p->zw = false;
+      if (const char* e = std::getenv("CPB_ZW")) p->zw = zw_ok && std::atoi(e) != 0;
     }
     {
       // mirror-pair x kernels: the mirror of internal ray r must be ray nrays - 1 - r (true whenever the ray

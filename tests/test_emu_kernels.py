@@ -41,27 +41,31 @@ def test_kernels_match_oracle(emu_cdll, n, nstate, mb, fp):
 
 @pytest.mark.parametrize("n,radix", [(16, (4, 4)), (32, (8, 4)), (48, (12, 4)), (64, (8, 8))])
 def test_warp_z_kernels_selected_and_match_block_kernels(emu_cdll, monkeypatch, n, radix):
-    """The warp-autonomous z kernels (kernels_zw.h) are the default where the length has a CPB_ZW
-    factorisation and the band fits; CPB_ZW=0 falls back to the block kernels, same results (both are
-    compared with the oracle in test_kernels_match_oracle; here with each other, incl. odd state counts,
-    several batches and a pair group split)."""
+    """The warp-autonomous z kernels (kernels_zw.h, selected with CPB_ZW=1 where the length has a CPB_ZW
+    factorisation and the band fits) against the block kernels and the oracle, incl. odd state counts and
+    several batches."""
     d = synthetic.make_inputs(n, 5, f_pattern="mixed")
+    monkeypatch.setenv("CPB_ZW", "1")
     p = _plan(d, emu_cdll, max_batch=2)
     assert p.info["z_warp_kernels"] and p.info["z_warp_radix"] == radix
     monkeypatch.setenv("CPB_ZW", "0")
     q = _plan(d, emu_cdll, max_batch=2)
     monkeypatch.delenv("CPB_ZW")
     assert not q.info["z_warp_kernels"] and q.info["z_warp_radix"] == (0, 0)
+    geo = orc.make_geometry(n)
     rho_w, ekin_w, *_ = p.rhoofr(d["c0"], d["f"])
+    assert relmax(rho_w, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
     rho_b, ekin_b, *_ = q.rhoofr(d["c0"], d["f"])
     assert relmax(rho_w, rho_b) < 1e-13 and abs(ekin_w - ekin_b) < ETOL
     c2w, c2b = 0.5 * d["c0"], 0.5 * d["c0"]
     p.vpsi(d["c0"], c2w, d["f"], d["vpot"])
     q.vpsi(d["c0"], c2b, d["f"], d["vpot"])
     assert relmax(c2w, c2b) < 1e-13
+    assert relmax(c2w, orc.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
 
 
-def test_warp_z_kernels_not_used_without_factorisation(emu_cdll):
+def test_warp_z_kernels_not_used_without_factorisation(emu_cdll, monkeypatch):
+    monkeypatch.setenv("CPB_ZW", "1")
     d = synthetic.make_inputs(20, 2)
     assert not _plan(d, emu_cdll).info["z_warp_kernels"]
 

@@ -709,3 +709,30 @@ def test_hfx_full_size_identities(dev):
     z2 = torch.zeros_like(c0)
     e2, v2 = pw.hfx_dev(pdn, c0, z2, d["f"], sc)
     assert (e2, v2) == (e, v) and torch.equal(z, z2)
+
+
+@pytest.mark.parametrize("n,nstate,mb,radix", [(16, 5, 2, (4, 4)), (48, 5, 2, (12, 4)), (64, 6, 4, (8, 8)),
+                                               (96, 7, 4, (12, 8)), (128, 4, 2, (16, 8)), (144, 2, 2, (12, 12)),
+                                               (192, 9, 4, (24, 8)), (256, 2, 2, (16, 16))])
+def test_warp_z_kernels_match_block_kernels_and_oracle(dev, monkeypatch, n, nstate, mb, radix):
+    """k_zw_rho / k_zw_vpsi (kernels_zw.h, CPB_ZW=1): same rho and C2 as the block kernels to rounding, and
+    within the north-star tolerance of the oracle (NumPy up to 112, staged C oracle above)."""
+    d = synthetic.make_inputs(n, nstate, f_pattern="mixed")
+    monkeypatch.setenv("CPB_ZW", "1")
+    pw = Plan(d["nr"], d["inyh"], d["hg"], max_batch=mb)
+    monkeypatch.setenv("CPB_ZW", "0")
+    pb = Plan(d["nr"], d["inyh"], d["hg"], max_batch=mb)
+    monkeypatch.delenv("CPB_ZW")
+    assert pw.info["z_warp_kernels"] and pw.info["z_warp_radix"] == radix and not pb.info["z_warp_kernels"]
+    rho_w, sw, c2_w = _dev_run(pw, d, dev)
+    rho_b, sb, c2_b = _dev_run(pb, d, dev)
+    assert relmax(rho_w, rho_b) < 1e-13 and relmax(c2_w, c2_b) < 1e-13
+    assert abs(sw[0] - sb[0]) < ETOL * max(1.0, abs(sb[0])) and abs(sw[2] - sb[2]) < ETOL
+    if n <= 112:
+        geo = orc.make_geometry(n)
+        assert relmax(rho_w, orc.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+        assert relmax(c2_w, orc.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
+    else:
+        geo = orc.make_geometry(n)
+        assert relmax(rho_w, staged.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+        assert relmax(c2_w, staged.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
