@@ -113,7 +113,8 @@ class Plan:
                     radix=tuple((inf.radix[d][0], inf.radix[d][1]) for d in range(3)),
                     workspace_bytes=inf.workspace_bytes,
                     band_pruned=tuple(inf.band_pruned), chunk_xtiles=inf.chunk_xtiles, streams=inf.streams,
-                    z_warp_kernels=bool(inf.z_warp_kernels), z_warp_radix=tuple(inf.z_warp_radix))
+                    z_warp_kernels=bool(inf.z_warp_kernels), z_warp_radix=tuple(inf.z_warp_radix),
+                    x_warp_kernels=inf.x_warp_kernels, x_warp_radix=inf.x_warp_radix)
 
     def maps(self):
         """(nzhs, indzs) with the reference's numbering (fftprp_utils.mod.F90:269-285)."""

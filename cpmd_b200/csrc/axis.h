@@ -4,6 +4,7 @@
 #pragma once
 #include "kernels.h"
 #include "kernels_zw.h"
+#include "kernels_xw.h"
 
 namespace cpb {
 
@@ -43,6 +44,16 @@ struct AxisKernels {
                 int xt0, int nxc, bool half);
   void (*z_vpsi)(cudaStream_t, cplx* T2, const double* vpot, const PlanDev&, int npair, int xt0, int nxc,
                  int ppg, bool half);
+  // warp-autonomous mirror-pair x passes (kernels_xw.h); null if the length has no CPB_XW factorisation.
+  // Band-pruned only: usable when the x band lies inside [8*xw_klo, 8*xw_khi).  kin partials: [pair][units][4]
+  void (*x_inv_w)(cudaStream_t, const cplx* c0, long ldc, cplx* T1, const PlanDev&, const PairDev&, int npair,
+                  int ppg, double* kin_part, int geq0);
+  void (*x_fwd_w)(cudaStream_t, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev&, const PairDev&,
+                  int npair, int ppg, bool acc);
+  int xw_ra, xw_klo, xw_khi;
+  int xw_rays;            // rays per warp (each warp also owns their mirrors)
+  int xw_warps;           // warps per block
+  int xw_inv_blocks, xw_fwd_blocks;  // occupancy the kernels are compiled for
   // warp-autonomous z passes (kernels_zw.h); null if the length has no CPB_ZW factorisation.  Band-pruned
   // only: usable when the z band lies inside [zw_rb*zw_klo, zw_rb*zw_khi)
   void (*z_rho_w)(cudaStream_t, const cplx* T2, double* rho, const PlanDev&, const PairDev&, int npair,

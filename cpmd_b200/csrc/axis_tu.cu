@@ -51,7 +51,7 @@ void x_inv_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev&
   auto k = k_x_inv<R1, R2, SL, B, HALF, false>;
   const size_t smem = C::smem_inv(KRange<R1, HALF>::cnt);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg,
+  CPB_LAUNCH_PDL(0, k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg,
              (const double*)nullptr);
 }
 void x_inv(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
@@ -67,7 +67,7 @@ void x_inv_gk_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanD
   auto k = k_x_inv<R1, R2, SL, B, HALF, true>;
   const size_t smem = C::smem_inv(KRange<R1, HALF>::cnt);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg, gk);
+  CPB_LAUNCH_PDL(0, k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), smem, st, c0, ldc, T1, pd, pr, npair, ppg, gk);
 }
 void x_inv_gk(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
               int ppg, bool half, const double* gk) {
@@ -80,7 +80,7 @@ void x_fwd_t(cudaStream_t st, const cplx* T1, cplx* G, const PlanDev& pd, int np
   using C = XCfg<R1, R2, SL>;
   auto k = k_x_fwd<R1, R2, SL, B, HALF>;
   allow_smem(k, C::SMEM_FWD);
-  CPB_LAUNCH(k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_FWD, st, T1, G, pd, npair, ppg);
+  CPB_LAUNCH_PDL(5, k, dim3(pd.nrp / SL, (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_FWD, st, T1, G, pd, npair, ppg);
 }
 void x_fwd(cudaStream_t st, const cplx* T1, cplx* G, const PlanDev& pd, int npair, int ppg, bool half) {
   if (half) x_fwd_t<true>(st, T1, G, pd, npair, ppg);
@@ -97,7 +97,7 @@ void x_inv_m_t(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDe
   using M = XMCfg<R1, R2, SL, HALF>;
   auto k = k_x_inv_m<R1, R2, SL, B, HALF, KIN>;
   allow_smem(k, M::SMEM_INV);
-  CPB_LAUNCH(k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_INV, st, c0, ldc, T1, pd, pr,
+  CPB_LAUNCH_PDL(0, k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_INV, st, c0, ldc, T1, pd, pr,
              npair, ppg, kin_part, geq0);
 }
 void x_inv_m(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
@@ -118,7 +118,7 @@ void x_fwd_m_t(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long l
   using M = XMCfg<R1, R2, SL, HALF>;
   auto k = k_x_fwd_m<R1, R2, SL, B, HALF, ACC>;
   allow_smem(k, M::SMEM_FWD);
-  CPB_LAUNCH(k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_FWD, st, T1, c0, c2, ldc, pd, pr,
+  CPB_LAUNCH_PDL(5, k, dim3(x_m_blocks(pd), (npair + ppg - 1) / ppg), dim3(C::NT), M::SMEM_FWD, st, T1, c0, c2, ldc, pd, pr,
              npair, ppg);
 }
 void x_fwd_m(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev& pd, const PairDev& pr,
@@ -139,7 +139,7 @@ void y_inv_t(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int n
   auto k = k_y_inv<R1, R2, B, HALF, CPB_YINV_XB>;
   const size_t smem = YZCfg<R1, R2, B>::smem(pd.nyb * B, CPB_YINV_XB);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
+  CPB_LAUNCH_PDL(1, k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
              dim3(B * RM), smem, st, T1, T2, pd, xt0, npair, ppg);
 }
 void y_inv(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
@@ -152,7 +152,7 @@ template <bool HALF>
 void y_fwd_t(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg) {
   auto k = k_y_fwd<R1, R2, B, HALF>;
   allow_smem(k, kSmemYZ2);
-  CPB_LAUNCH(k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
+  CPB_LAUNCH_PDL(4, k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
              dim3(B * RM), kSmemYZ2, st, T2, T1, pd, xt0, npair, ppg);
 }
 void y_fwd(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
@@ -167,7 +167,7 @@ void z_rho_t(cudaStream_t st, const cplx* T2, double* rho, const PlanDev& pd, co
   auto k = k_z_rho<R1, R2, B, HALF, CPB_ZRHO_XB>;
   const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B, CPB_ZRHO_XB);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), smem, st, T2, rho, pd, pr, npair, xt0);
+  CPB_LAUNCH_PDL(2, k, dim3(nxc, pd.n2), dim3(B * RM), smem, st, T2, rho, pd, pr, npair, xt0);
 }
 void z_rho(cudaStream_t st, const cplx* T2, double* rho, const PlanDev& pd, const PairDev& pr, int npair,
            int xt0, int nxc, bool half) {
@@ -181,13 +181,61 @@ void z_vpsi_t(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, 
   auto k = k_z_vpsi<R1, R2, B, HALF>;
   const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B);
   allow_smem(k, smem);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T2, vpot, pd, xt0, npair, ppg);
+  CPB_LAUNCH_PDL(3, k, dim3(nxc, pd.n2, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T2, vpot, pd, xt0, npair, ppg);
 }
 void z_vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
             int ppg, bool half) {
   if (half) z_vpsi_t<true>(st, T2, vpot, pd, npair, xt0, nxc, ppg);
   else z_vpsi_t<false>(st, T2, vpot, pd, npair, xt0, nxc, ppg);
 }
+
+// warp-autonomous mirror-pair x passes (kernels_xw.h), band-pruned instantiation only
+constexpr bool kHasXW = XWPick<N>::ra != 0 && B == 8;
+template <bool HAS, int DUMMY = 0>
+struct XWLaunch {
+  static constexpr void (*inv)(cudaStream_t, const cplx*, long, cplx*, const PlanDev&, const PairDev&, int, int, double*,
+                               int) = nullptr;
+  static constexpr void (*fwd)(cudaStream_t, const cplx*, const cplx*, cplx*, long, const PlanDev&, const PairDev&, int,
+                               int, bool) = nullptr;
+  static constexpr int ra = 0, klo = 0, khi = 0, rays = 0, warps = 0, inv_blocks = 0, fwd_blocks = 0;
+};
+template <int DUMMY>
+struct XWLaunch<true, DUMMY> {  // partial specialisation: members are only instantiated where used
+  static constexpr int ra = XWPick<N>::ra ? XWPick<N>::ra : 8;
+  using C = XWCfg<ra, true>;
+  static constexpr int klo = C::KR::lo, khi = C::KR::hi, rays = C::H, warps = C::WARPS, inv_blocks = C::MINB_INV,
+                       fwd_blocks = C::MINB_FWD;
+  static int grid_x(const PlanDev& pd) { return (xw_units<ra, true>(pd.nrays) + warps - 1) / warps; }
+  static void inv(cudaStream_t st, const cplx* c0, long ldc, cplx* T1, const PlanDev& pd, const PairDev& pr, int npair,
+                  int ppg, double* kin_part, int geq0) {
+    if (kin_part) {
+      auto k = k_xw_inv<ra, B, true, true>;
+      allow_smem(k, C::SMEM_INV);
+      CPB_LAUNCH_PDL(0, k, dim3(grid_x(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_INV, st, c0, ldc, T1, pd, pr, npair,
+                 ppg, kin_part, geq0);
+    } else {
+      auto k = k_xw_inv<ra, B, true, false>;
+      allow_smem(k, C::SMEM_INV);
+      CPB_LAUNCH_PDL(0, k, dim3(grid_x(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_INV, st, c0, ldc, T1, pd, pr, npair,
+                 ppg, kin_part, geq0);
+    }
+  }
+  static void fwd(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long ldc, const PlanDev& pd,
+                  const PairDev& pr, int npair, int ppg, bool acc) {
+    if (acc) {
+      auto k = k_xw_fwd<ra, B, true, true>;
+      allow_smem(k, C::SMEM_FWD);
+      CPB_LAUNCH_PDL(5, k, dim3(grid_x(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_FWD, st, T1, c0, c2, ldc, pd, pr,
+                 npair, ppg);
+    } else {
+      auto k = k_xw_fwd<ra, B, true, false>;
+      allow_smem(k, C::SMEM_FWD);
+      CPB_LAUNCH_PDL(5, k, dim3(grid_x(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM_FWD, st, T1, c0, c2, ldc, pd, pr,
+                 npair, ppg);
+    }
+  }
+};
+using XWL = XWLaunch<kHasXW>;
 
 // warp-autonomous z passes (kernels_zw.h), band-pruned instantiation only
 using ZP = ZWPick<N>;
@@ -208,13 +256,13 @@ struct ZWLaunch<true, DUMMY> {  // partial specialisation: members are only inst
                   int xt0, int nxc) {
     auto k = k_zw_rho<ra, rb, L, B, true>;
     allow_smem(k, C::SMEM);
-    CPB_LAUNCH(k, dim3(nxc, grid_y(pd)), dim3(C::NT), C::SMEM, st, T2, rho_, pd, pr, npair, xt0);
+    CPB_LAUNCH_PDL(2, k, dim3(nxc, grid_y(pd)), dim3(C::NT), C::SMEM, st, T2, rho_, pd, pr, npair, xt0);
   }
   static void vpsi(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
                    int ppg) {
     auto k = k_zw_vpsi<ra, rb, L, B, true>;
     allow_smem(k, C::SMEM);
-    CPB_LAUNCH(k, dim3(nxc, grid_y(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM, st, T2, vpot, pd, xt0, npair,
+    CPB_LAUNCH_PDL(3, k, dim3(nxc, grid_y(pd), (npair + ppg - 1) / ppg), dim3(C::NT), C::SMEM, st, T2, vpot, pd, xt0, npair,
                ppg);
   }
 };
@@ -225,7 +273,7 @@ void z_fwd_real_t(cudaStream_t st, const double* fre, const double* fim, cplx* T
                   int nxc, const double* mul, double scale) {
   auto k = k_z_fwd_real<R1, R2, B, HALF>;
   allow_smem(k, kSmemYZ);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, fre, fim, T2, pd, xt0, mul, scale);
+  CPB_LAUNCH_PDL(6, k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, fre, fim, T2, pd, xt0, mul, scale);
 }
 void z_fwd_real(cudaStream_t st, const double* fre, const double* fim, cplx* T2, const PlanDev& pd, int xt0, int nxc,
                 bool half, const double* mul, double scale) {
@@ -238,7 +286,7 @@ void z_inv_real_t(cudaStream_t st, const cplx* T2, double* ore, double* oim, con
                   bool acc) {
   auto k = k_z_inv_real<R1, R2, B, HALF>;
   allow_smem(k, kSmemYZ);
-  CPB_LAUNCH(k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, T2, ore, oim, pd, xt0, acc ? 1 : 0);
+  CPB_LAUNCH_PDL(6, k, dim3(nxc, pd.n2), dim3(B * RM), kSmemYZ, st, T2, ore, oim, pd, xt0, acc ? 1 : 0);
 }
 void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const PlanDev& pd, int xt0, int nxc,
                 bool acc, bool half) {
@@ -248,6 +296,8 @@ void z_inv_real(cudaStream_t st, const cplx* T2, double* ore, double* oim, const
 
 const AxisKernels kTable = {N, R1, R2, B, SL, KRange<R1, true>::lo, KRange<R1, true>::hi,
                             x_inv, x_inv_gk, x_fwd, x_inv_m, x_fwd_m, y_inv, y_fwd, z_rho, z_vpsi,
+                            XWL::inv, XWL::fwd, XWL::ra, XWL::klo, XWL::khi, XWL::rays, XWL::warps, XWL::inv_blocks,
+                            XWL::fwd_blocks,
                             ZWL::rho, ZWL::vpsi, ZWL::ra, ZWL::rb, ZWL::klo, ZWL::khi, ZWL::upr, ZWL::warps, ZWL::minb,
                             z_fwd_real, z_inv_real,
                             YZBlocks<R1, R2>::v, XCfg<R1, R2, SL>::MINB, XCfg<R1, R2, SL>::MINB_FWD,

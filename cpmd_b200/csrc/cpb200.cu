@@ -15,6 +15,22 @@
 
 using namespace cpb;
 
+#if !defined(CPB_EMULATE)
+namespace cpb {
+constexpr unsigned kPdlDefaultMask = 0x2fu;  // not y_fwd: starting it under the tail of k_z_vpsi costs 0.09 ms per launch (profiles/r02p_probe_pdl_mask.txt)
+// programmatic dependent launch of the hot-path kernels (cpb_defs.h): bit c of CPB_PDL allows kernels of class c
+// (0 x_inv, 1 y_inv, 2 z_rho, 3 z_vpsi, 4 y_fwd, 5 x_fwd, 6 dense z) to become resident before their predecessor
+// on the stream has finished
+unsigned pdl_mask() {
+  static const unsigned mask = [] {
+    const char* e = std::getenv("CPB_PDL");
+    return e ? (unsigned)std::strtoul(e, nullptr, 0) : kPdlDefaultMask;
+  }();
+  return mask;
+}
+}  // namespace cpb
+#endif
+
 namespace {
 thread_local std::string g_last_error;
 
@@ -95,6 +111,7 @@ struct cpb_plan {
   double tpiba2 = 0, omega = 0;
   int device = 0;
   int max_batch = 32;
+  bool auto_batch = false;  // max_batch_pairs <= 0: sized from the work space of one pair once the ray table is known
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
   int n_sm = 148;
@@ -112,6 +129,8 @@ struct cpb_plan {
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
   bool half_x = false, half_y = false, half_z = false;  // band-pruned kernel variants usable
+  bool xw_inv = false, xw_fwd = false;  // x passes run the warp-autonomous mirror-pair kernels (kernels_xw.h)
+  int nux_w = 0;                        // their units (warps) per pair group
   bool zw = false;  // z passes of the wavefunction path run the warp-autonomous kernels (kernels_zw.h)
   bool mirror = false;        // mirror-pair x kernels usable (ray numbering mirror-symmetric; CPB_X_MIRROR=0 disables)
   int nbx_m = 0;              // their blocks per pair group
@@ -405,6 +424,13 @@ int ew_ppg(const cpb_plan* p, int npair, int waves) {
 void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, const PairDev& prb, int nb, int off = 0) {
   cudaStream_t st = w.s;
   Timed t(p, st, CPB_K_X_INV);
+  if (p->xw_inv && !p->kpt_mode) {
+    double* kin = p->kin_cur ? p->kin_cur + (size_t)off * p->nux_w * 4 : nullptr;
+    const int blocks = (p->nux_w + p->kx->xw_warps - 1) / p->kx->xw_warps;
+    p->kx->x_inv_w(st, c0, ldc, w.T1, p->pd, prb, nb,
+                   pairs_per_group(p, nb, blocks, p->kx->xw_inv_blocks, p->prologue_pairs_x), kin, p->geq0);
+    return;
+  }
   if (p->mirror && !p->kpt_mode) {
     double* kin = p->kin_cur ? p->kin_cur + (size_t)off * p->nbx_m * 4 : nullptr;
     p->kx->x_inv_m(st, c0, ldc, w.T1, p->pd, prb, nb,
@@ -423,7 +449,7 @@ void kin_begin(cpb_plan* p, int npairs, int nblk, cudaStream_t st) {
     rt::dfree(p->d_kinpart);
     p->d_kinpart = nullptr;
     p->kinpart_cap = 0;
-    p->d_kinpart = (double*)rt::dmalloc((size_t)npairs * p->nbx_m * 4 * sizeof(double));
+    p->d_kinpart = (double*)rt::dmalloc((size_t)npairs * std::max(p->nbx_m, p->nux_w) * 4 * sizeof(double));
     p->kinpart_cap = (size_t)npairs;
   }
   rt::dzero(p->d_red, (size_t)kRedPerState * nblk * sizeof(double), st);
@@ -435,8 +461,8 @@ bool kin_end(cpb_plan* p, const PairDev& pr, int npairs, int first, cudaStream_t
   p->kin_cur = nullptr;
   auto k = k_kin_reduce;
   Timed t(p, st, CPB_K_KIN);
-  CPB_LAUNCH(k, dim3(npairs), dim3(128), 4 * 128 * sizeof(double), st, (const double*)p->d_kinpart, p->nbx_m, pr, first,
-             p->d_red);
+  CPB_LAUNCH(k, dim3(npairs), dim3(128), 4 * 128 * sizeof(double), st, (const double*)p->d_kinpart,
+             p->xw_inv ? p->nux_w : p->nbx_m, pr, first, p->d_red);
   return true;
 }
 
@@ -446,6 +472,13 @@ bool kin_end(cpb_plan* p, const PairDev& pr, int npairs, int first, cudaStream_t
 void run_x_fwd(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, cplx* c2, long ldc, const PairDev& prb, int nb,
                bool accumulate) {
   cudaStream_t st = w.s;
+  if (p->xw_fwd && !p->kpt_mode) {
+    Timed t(p, st, CPB_K_X_FWD);
+    const int blocks = (p->nux_w + p->kx->xw_warps - 1) / p->kx->xw_warps;
+    p->kx->x_fwd_w(st, w.T1, c0, c2, ldc, p->pd, prb, nb,
+                   pairs_per_group(p, nb, blocks, p->kx->xw_fwd_blocks, p->prologue_pairs_x), accumulate);
+    return;
+  }
   if (p->mirror && !p->kpt_mode) {
     // Gamma point: forward x pass fused with the unpack (no band-ray storage, one launch per batch)
     Timed t(p, st, CPB_K_X_FWD);
@@ -775,6 +808,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->omega = omega;
     p->device = device;
     p->max_batch = std::min(max_batch_pairs > 0 ? max_batch_pairs : 32, (int)kMaxGroup);
+    p->auto_batch = max_batch_pairs <= 0;
     p->kx = find_axis_kernels(nr[0]);
     p->ky = find_axis_kernels(nr[1]);
     p->kz = find_axis_kernels(nr[2]);
@@ -921,6 +955,14 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
         if (!std::atoi(e)) p->mirror = false;
       }
       p->nbx_m = ((nrays + 1) / 2 + SL / 2 - 1) / (SL / 2);
+      // warp-autonomous variants: band-pruned only, own factorisation of n1 (RB = 8)
+      const bool xw_ok = p->mirror && p->half_x && p->kx->x_inv_w && xlo >= 8 * p->kx->xw_klo && xhi < 8 * p->kx->xw_khi;
+      if (xw_ok) p->nux_w = ((nrays + 1) / 2 + p->kx->xw_rays - 1) / p->kx->xw_rays;
+      if (const char* e = std::getenv("CPB_XW")) {
+        const int v = std::atoi(e);  // bit 0: inverse, bit 1: forward
+        p->xw_inv = xw_ok && (v & 1);
+        p->xw_fwd = xw_ok && (v & 2) && p->kx->x_fwd_w;
+      }
     }
     p->xlo = xlo;
     p->xhi = xhi;
@@ -962,9 +1004,17 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("CPB_PROLOGUE")) p->prologue_pairs = std::max(0.0, std::atof(e));
     if (const char* e = std::getenv("CPB_PROLOGUE_X")) p->prologue_pairs_x = std::max(0.0, std::atof(e));
-    p->x_sub = std::min(p->x_sub, p->max_batch);
     p->g_pair = (size_t)nxb * nrp;
     p->t2_pair = (size_t)p->nxt * n2 * nzb * Bx;
+    if (p->auto_batch) {
+      // default batch: about 3 GB of T1 + T2, a multiple of 8 pairs in [8, 64].  Measured on B200
+      // (profiles/r02n_probe_batch.txt): small meshes gain from long batches (96^3: 1.12 -> 1.02 ms per step with
+      // 64 instead of 32 pairs, 120^3: 2.19 -> 2.04), 192^3 is flat between 32 and 64
+      const double per_pair = (double)(p->t1_pair + p->t2_pair) * sizeof(cplx);
+      const int fit = (int)(3.0e9 / std::max(per_pair, 1.0));
+      p->max_batch = std::max(8, std::min((int)kMaxGroup, fit / 8 * 8));
+    }
+    p->x_sub = std::min(p->x_sub, p->max_batch);
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
@@ -1067,6 +1117,8 @@ int cpb_plan_get_info(const cpb_plan* p, cpb_plan_info* info) {
   info->z_warp_kernels = p->zw ? 1 : 0;
   info->z_warp_radix[0] = p->zw ? p->kz->zw_ra : 0;
   info->z_warp_radix[1] = p->zw ? p->kz->zw_rb : 0;
+  info->x_warp_kernels = (p->xw_inv ? 1 : 0) | (p->xw_fwd ? 2 : 0);
+  info->x_warp_radix = (p->xw_inv || p->xw_fwd) ? p->kx->xw_ra : 0;
   return CPB_OK;
 }
 

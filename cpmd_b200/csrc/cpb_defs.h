@@ -23,6 +23,7 @@
 #define CPB_SHARED static thread_local
 #define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
   ::emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#define CPB_LAUNCH_PDL(cls, kern, grid, block, smem, stream, ...) CPB_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>
 #define CPB_HD __host__ __device__ __forceinline__
@@ -36,6 +37,10 @@
 #define CPB_SHARED __shared__
 #define CPB_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// launch with programmatic stream serialisation (see pdl_wait below); only for kernels that call pdl_wait()
+// cls: kernel class 0..6 (x_inv, y_inv, z_rho, z_vpsi, y_fwd, x_fwd, dense z), bit of the CPB_PDL mask
+#define CPB_LAUNCH_PDL(cls, kern, grid, block, smem, stream, ...) \
+  ::cpb::launch_pdl((cls), (kern), (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
 namespace cpb {
@@ -81,6 +86,40 @@ CPB_D cplx ld_stream(const cplx* p) { return __ldcs(p); }
 // TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned address) into L2
 CPB_D void l2_prefetch(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The kernels of a batch form a chain on one stream, each consuming what the
+// previous one wrote; between two of them the SMs drain (last wave of the producer), the front end launches
+// the consumer and its blocks run their prologue (twiddle table, index tables, barrier set-up) - a few
+// microseconds, several hundred times per CP step.  Kernels launched with CPB_LAUNCH_PDL may become resident
+// as soon as every block of the preceding kernel has called pdl_trigger() (first statement of every hot-path
+// kernel), i.e. while its last wave is still running; they do the part of their prologue that only reads
+// plan constants and then pdl_wait(): that returns when the preceding kernel has completed and its writes are
+// visible.  Everything produced by earlier work on the stream is touched after pdl_wait() only.  Both are
+// no-ops when the kernel was launched without the attribute (CPB_PDL=0) and in the simulator build.
+// ---------------------------------------------------------------------------------------------
+#if defined(CPB_EMULATE)
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
+#else
+CPB_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+CPB_D void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+unsigned pdl_mask();  // cpb200.cu: kernel classes that may start early (CPB_PDL environment switch)
+template <class... KArgs, class... Args>
+inline void launch_pdl(int cls, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = ((pdl_mask() >> cls) & 1u) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 #endif
 

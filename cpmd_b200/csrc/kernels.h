@@ -239,7 +239,9 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB))
   const int rayB = blockIdx.x * SL + slotB;
   const bool okB = slotB < SL && rayB < pd.nrays;
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
+  pdl_trigger();
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw1[i];
+  pdl_wait();  // everything below may touch what the preceding kernel produced (or still reads: T1)
   // my band positions -> plane-wave index (bit 31: -G partner) or kNoPW
   uint32_t tab[KR::cnt];
   static_for<0, KR::cnt>([&](auto kk) {
@@ -324,6 +326,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD
   using KR = KRange<R1, HALF>;
   constexpr int P1 = C::P1;
   CPB_DYN_SMEM(cplx, S);
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
@@ -463,6 +467,9 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  pdl_trigger();
+  for (int i = tid; i < N; i += NT) TW[i] = pd.tw1[i];
+  pdl_wait();  // everything below may touch what the preceding kernel produced (or still reads: T1)
   for (int i = tid; i < p1 - p0; i += NT) {
     PS1[i] = __ldg(&pr.st1[p0 + i]);
     PS2[i] = __ldg(&pr.st2[p0 + i]);
@@ -480,7 +487,6 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   const bool okB = slotB < SL && sb.valid;
   const int spA = sa.self ? slotA : (slotA + H) % SL;    // slot that stages my -G partners
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
-  for (int i = tid; i < N; i += NT) TW[i] = pd.tw1[i];
   // my band positions -> plane-wave index (bit 31: -G partner) or kNoPW
   uint32_t tab[KR::cnt];
   double hgv[NPOS];
@@ -635,13 +641,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
+  pdl_trigger();
+  for (int i = tid; i < C::N; i += NT) TW[i] = pd.tw1[i];
+  pdl_wait();  // everything below may touch what the preceding kernel produced
   for (int i = tid; i < p1 - p0; i += NT) {
     PS1[i] = __ldg(&pr.st1[p0 + i]);
     PS2[i] = __ldg(&pr.st2[p0 + i]);
     PCA[i] = __ldg(&pr.ca[p0 + i]);
     PCB[i] = __ldg(&pr.cb[p0 + i]);
   }
-  for (int i = tid; i < C::N; i += NT) TW[i] = pd.tw1[i];
 #if CPB_X_ROT
   const int tidA = (NT % 32 == 0) ? (int)((tid + 32 * (blockIdx.x % (NT / 32))) % NT) : tid;  // see k_x_inv
 #else
@@ -856,11 +864,13 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
   const size_t t2_pair = (size_t)nxc * N * pd.nzb * B;
   const cplx* src = T1 + ((size_t)(xt0 + xtc) * pd.nrays + pd.rayoff[zr]) * B;
   cplx* dst = T2 + ((size_t)xtc * N * pd.nzb + zr) * B + b;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw2[i];
+  pdl_wait();  // T1 comes from the preceding kernel; T2 may still be read by it
   __syncthreads();
   if (tid == 0 && ny > 0) {
     for (int s = 0; s < kStages && p0 + s < p1; ++s) {
@@ -917,6 +927,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   constexpr int N = R1 * R2;
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
+  pdl_trigger();
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
 #if CPB_Y_ZFAST
@@ -934,6 +945,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
   const size_t t2_pair = (size_t)nxc * N * pd.nzb * B;
   const size_t ystride = (size_t)pd.nzb * B;
+  pdl_wait();  // T2 comes from the preceding kernel
   const cplx* src = T2 + ((size_t)xtc * N * pd.nzb + zr) * B + b;
   cplx* dst = T1 + ((size_t)(xt0 + xtc) * pd.nrays + pd.rayoff[zr]) * B + b;
   cplx nv[R2];
@@ -997,11 +1009,13 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
   const size_t pstride = (size_t)nxc * pd.n2 * pd.nzb * B;
   const cplx* tile = T2 + ((size_t)xtc * pd.n2 + y) * pd.nzb * B;
   const int zlo = pd.zlo, nzb = pd.nzb;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw3[i];
+  pdl_wait();  // T2 and rho come from preceding kernels
   // the accumulators start from rho itself: the read-modify-write's read overlaps the first tile
   double acc[R2];
   static_for<0, R2>([&](auto qq) {
@@ -1093,11 +1107,13 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   const size_t pstride = (size_t)nxc * pd.n2 * pd.nzb * B;
   cplx* tile = T2 + ((size_t)xtc * pd.n2 + y) * pd.nzb * B;
   const int zlo = pd.zlo, nzb = pd.nzb;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw3[i];
+  pdl_wait();  // T2 (and possibly V) come from preceding kernels
   double vv[R2];
   static_for<0, R2>([&](auto qq) {
     constexpr int q = decltype(qq)::value;
@@ -1183,6 +1199,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
                  int xt0, const double* CPB_RESTRICT mul, double scale) {
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
   const int xtc = blockIdx.x;
@@ -1227,6 +1245,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, 2)
     k_z_inv_real(const cplx* CPB_RESTRICT T2, double* ore, double* oim, PlanDev pd, int xt0, int acc) {
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int b = tid % B, r = tid / B;
   const int xtc = blockIdx.x;

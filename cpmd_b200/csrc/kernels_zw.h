@@ -148,10 +148,12 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((ZWCfg<RA, RB, L, HALF>::NT), (ZWCfg<RA, RB, L, HAL
   cplx* EX = S + (size_t)w * C::EX_ELEMS;
   cplx* ST = S + (size_t)C::WARPS * C::EX_ELEMS + (size_t)w * C::ST_ELEMS;
   cplx* TW = S + (size_t)C::WARPS * (C::EX_ELEMS + C::ST_ELEMS);
+  pdl_trigger();
   for (int i = tid; i < N; i += C::NT) {
     const int p = i / RB, a = i % RB;
     TW[C::pos(p, a)] = pd.tw3[a * p];
   }
+  pdl_wait();  // T2, rho / V come from preceding kernels
   __syncthreads();  // the only block barrier: twiddles visible
   const int unit = blockIdx.y * C::WARPS + w;
   const int y = unit / HV, hv = unit % HV;
@@ -234,10 +236,12 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((ZWCfg<RA, RB, L, HALF>::NT), (ZWCfg<RA, RB, L, HAL
   cplx* EX = S + (size_t)w * C::EX_ELEMS;
   cplx* ST = S + (size_t)C::WARPS * C::EX_ELEMS + (size_t)w * C::ST_ELEMS;
   cplx* TW = S + (size_t)C::WARPS * (C::EX_ELEMS + C::ST_ELEMS);
+  pdl_trigger();
   for (int i = tid; i < N; i += C::NT) {
     const int p = i / RB, a = i % RB;
     TW[C::pos(p, a)] = pd.tw3[a * p];
   }
+  pdl_wait();  // T2, rho / V come from preceding kernels
   __syncthreads();  // the only block barrier: twiddles visible
   const int unit = blockIdx.y * C::WARPS + w;
   const int y = unit / HV, hv = unit % HV;

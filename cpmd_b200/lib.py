@@ -49,6 +49,8 @@ class PlanInfo(C.Structure):
         ("streams", C.c_int),
         ("z_warp_kernels", C.c_int),
         ("z_warp_radix", C.c_int * 2),
+        ("x_warp_kernels", C.c_int),
+        ("x_warp_radix", C.c_int),
     ]
 
 

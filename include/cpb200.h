@@ -94,6 +94,8 @@ typedef struct {
   int streams;        /* work spaces / streams the batches of a call alternate between */
   int z_warp_kernels; /* 1: the z passes of rhoofr / vpsi run the warp-autonomous kernels (kernels_zw.h) */
   int z_warp_radix[2];/* their factorisation of n3 (band-side radix, real-space-side radix), 0 if unused */
+  int x_warp_kernels; /* bit 0: the inverse x pass runs the warp-autonomous kernel (kernels_xw.h), bit 1: the forward one */
+  int x_warp_radix;   /* their band-side radix of n1 (the other one is 8), 0 if unused */
 } cpb_plan_info;
 
 const char* cpb_last_error(void);
@@ -103,7 +105,8 @@ const char* cpb_version(void);
 int cpb_length_supported(int n);
 
 /* nr, kr: 3 ints each.  inyh: (3,ngw) column-major INTEGER*4, 1-based (cppt inyh).  hg: |G|^2 in
- * units of tpiba2.  device: CUDA ordinal.  max_batch_pairs: pairs per batch (<=0: default 32). */
+ * units of tpiba2.  device: CUDA ordinal.  max_batch_pairs: pairs per batch (<=0: sized
+ * from the mesh - about 3 GB of work space, a multiple of 8 in [8, 64]; 32 for the 192^3 north-star case). */
 int cpb_plan_create(cpb_plan** plan, const int* nr, const int* kr, int ngw, const int32_t* inyh,
                     const double* hg, double tpiba2, double omega, int device,
                     int max_batch_pairs);

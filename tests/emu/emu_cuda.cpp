@@ -146,3 +146,24 @@ void __syncwarp() {
   bs->current->wait = 2;
   swapcontext(&bs->current->ctx, &bs->sched);
 }
+
+// butterfly sum over the 32 fibers of a warp with the device's pairing order (x += shfl_xor(x, m), m = 16 .. 1)
+namespace cpb {
+void emu_warp_sum4(double (&q)[4]) {
+  static thread_local double scratch[64][32][4];
+  const unsigned t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const unsigned w = t / 32, lane = t % 32;
+  if (w >= 64) {
+    std::fprintf(stderr, "emu: warp_sum4 supports 64 warps per block\n");
+    std::abort();
+  }
+  for (int m = 16; m > 0; m >>= 1) {
+    for (int i = 0; i < 4; ++i) scratch[w][lane][i] = q[i];
+    __syncwarp();
+    double o[4];
+    for (int i = 0; i < 4; ++i) o[i] = scratch[w][lane ^ m][i];
+    __syncwarp();
+    for (int i = 0; i < 4; ++i) q[i] += o[i];
+  }
+}
+}  // namespace cpb

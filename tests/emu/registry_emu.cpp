@@ -2,7 +2,7 @@
 #include "axis.h"
 
 namespace cpb {
-#define CPB_EMU_SIZES(X) X(16) X(20) X(24) X(30) X(32) X(36) X(40) X(48) X(60) X(64) X(72)
+#define CPB_EMU_SIZES(X) X(16) X(20) X(24) X(30) X(32) X(36) X(40) X(48) X(60) X(64) X(72) X(128) X(192)
 #define X(N) const AxisKernels* axis_kernels_n##N();
 CPB_EMU_SIZES(X)
 #undef X

@@ -64,10 +64,56 @@ def test_warp_z_kernels_selected_and_match_block_kernels(emu_cdll, monkeypatch, 
     assert relmax(c2w, orc.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
 
 
+def test_default_batch_is_sized_from_the_mesh(emu_cdll):
+    """max_batch_pairs <= 0: a multiple of 8 pairs in [8, 64] (about 3 GB of work space); small meshes get 64."""
+    d = synthetic.make_inputs(16, 3)
+    assert _plan(d, emu_cdll, max_batch=0).info["max_batch"] == 64
+    assert _plan(d, emu_cdll, max_batch=5).info["max_batch"] == 5
+    p = _plan(d, emu_cdll, max_batch=0)
+    rho, *_ = p.rhoofr(d["c0"], d["f"])
+    assert relmax(rho, orc.rhoofr(orc.make_geometry(16), d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
+
+
 def test_warp_z_kernels_not_used_without_factorisation(emu_cdll, monkeypatch):
     monkeypatch.setenv("CPB_ZW", "1")
     d = synthetic.make_inputs(20, 2)
     assert not _plan(d, emu_cdll).info["z_warp_kernels"]
+
+
+def _stretched(nx, nyz):
+    """(nx, nyz, nyz) mesh whose cutoff ellipsoid fills the middle half of the long x axis: b1 shortened so that
+    |G|^2 < (nyz/4)^2 reaches x index nx/4 (exercises every band position of the x kernels at small cost)."""
+    nr = (nx, nyz, nyz)
+    b = np.diag([nyz / float(nx), 1.0, 1.0])
+    return nr, orc.make_geometry(nr, gcutw=(nyz / 4.0) ** 2, b=b)
+
+
+@pytest.mark.parametrize("nr_b,xw,ra", [((64, 64, 64), 1, 8), ("s128", 1, 16), ("s192", 1, 24), ("s192", 3, 24),
+                                        ((64, 64, 64), 3, 8)])
+def test_warp_x_kernels_match_oracle_and_block_kernels(emu_cdll, monkeypatch, nr_b, xw, ra):
+    """k_xw_inv / k_xw_fwd (kernels_xw.h, CPB_XW bit 0 / bit 1) against the oracle and the block mirror kernels:
+    rho, kin_energy / dotp sums folded into the gather, C2 with the += semantics, odd state count, several
+    batches and pair groups."""
+    if isinstance(nr_b, str):
+        nr, geo = _stretched(int(nr_b[1:]), 16)
+    else:
+        nr, geo = nr_b, orc.make_geometry(nr_b)
+    c0, f, v = orc.synthetic_inputs(geo, 5, f_pattern="mixed")
+    monkeypatch.setenv("CPB_XW", str(xw))
+    p = Plan(nr, geo.inyh, geo.hg, 1.0, 1.0, max_batch=2, _cdll=emu_cdll)
+    monkeypatch.setenv("CPB_XW", "0")
+    q = Plan(nr, geo.inyh, geo.hg, 1.0, 1.0, max_batch=2, _cdll=emu_cdll)
+    monkeypatch.delenv("CPB_XW")
+    assert p.info["x_warp_kernels"] == xw and p.info["x_warp_radix"] == ra and q.info["x_warp_kernels"] == 0
+    rho_w, ekin_w, rg_w, rr_w = p.rhoofr(c0, f)
+    rho_b, ekin_b, rg_b, rr_b = q.rhoofr(c0, f)
+    ref = orc.rhoofr(geo, c0, f, 1.0, 1.0)
+    assert relmax(rho_w, ref["rhoe"]) < RTOL and relmax(rho_w, rho_b) < 1e-13
+    assert abs(ekin_w - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"])) and abs(rg_w - ref["rsum_g"]) < ETOL
+    c2w, c2b = 0.5 * c0, 0.5 * c0
+    p.vpsi(c0, c2w, f, v)
+    q.vpsi(c0, c2b, f, v)
+    assert relmax(c2w, orc.vpsi(geo, c0, 0.5 * c0, f, v, 1.0)) < RTOL and relmax(c2w, c2b) < 1e-13
 
 
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])

@@ -736,3 +736,31 @@ def test_warp_z_kernels_match_block_kernels_and_oracle(dev, monkeypatch, n, nsta
         geo = orc.make_geometry(n)
         assert relmax(rho_w, staged.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)["rhoe"]) < RTOL
         assert relmax(c2_w, staged.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
+
+
+@pytest.mark.parametrize("n,nstate,mb,ra", [(64, 7, 4, 8), (128, 5, 2, 16), (192, 9, 4, 24)])
+def test_warp_x_kernels_match_block_kernels_and_oracle(dev, monkeypatch, n, nstate, mb, ra):
+    """k_xw_inv / k_xw_fwd (kernels_xw.h, CPB_XW=3): same rho, kinetic energy and C2 as the block mirror kernels
+    to rounding, and within the north-star tolerance of the oracle."""
+    d = synthetic.make_inputs(n, nstate, f_pattern="mixed")
+    monkeypatch.setenv("CPB_XW", "3")
+    pw = Plan(d["nr"], d["inyh"], d["hg"], max_batch=mb)
+    monkeypatch.setenv("CPB_XW", "0")
+    pb = Plan(d["nr"], d["inyh"], d["hg"], max_batch=mb)
+    monkeypatch.delenv("CPB_XW")
+    assert pw.info["x_warp_kernels"] == 3 and pw.info["x_warp_radix"] == ra and pb.info["x_warp_kernels"] == 0
+    rho_w, sw, c2_w = _dev_run(pw, d, dev)
+    rho_b, sb, c2_b = _dev_run(pb, d, dev)
+    assert relmax(rho_w, rho_b) < 1e-13 and relmax(c2_w, c2_b) < 1e-13
+    assert abs(sw[0] - sb[0]) < ETOL * max(1.0, abs(sb[0])) and abs(sw[1] - sb[1]) < ETOL and abs(sw[2] - sb[2]) < ETOL
+    geo = orc.make_geometry(n)
+    o = orc if n <= 112 else staged
+    ref = o.rhoofr(geo, d["c0"], d["f"], 1.0, 1.0)
+    assert relmax(rho_w, ref["rhoe"]) < RTOL and abs(sw[0] - ref["ekin"]) < ETOL * max(1.0, abs(ref["ekin"]))
+    assert relmax(c2_w, o.vpsi(geo, d["c0"], 0.5 * d["c0"], d["f"], d["vpot"], 1.0)) < RTOL
+    # overwrite mode (no c2 read)
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    v = torch.from_numpy(d["vpot"]).to(dev)
+    c2 = torch.full_like(c0, 3.0)
+    pw.vpsi_dev(c0, c2, d["f"], v, flags=lib.CPB_VPSI_OVERWRITE)
+    assert relmax(c2.cpu().numpy(), o.vpsi(geo, d["c0"], np.zeros_like(d["c0"]), d["f"], d["vpot"], 1.0)) < RTOL
