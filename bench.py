@@ -418,9 +418,9 @@ def run_ours(args, rank, world, local):
         rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
     _COLLECTIVES_USED["mode"] = collectives
     stream = torch.cuda.current_stream()
-    # the V broadcast runs on a side stream: only the first z pass of vpsi reads V (cpb_plan_set_vpot_event),
-    # so the gather and the x / y passes of the first batch overlap it.  In a CP step V derives from the
-    # group-summed rho, so the broadcast is ordered after the all-reduce.
+    # the exchanges run on a side stream: only the first z pass of vpsi reads V (cpb_plan_set_vpot_event), so
+    # the gather and the x / y passes of vpsi's first batch overlap them (CPB_BCAST_OVERLAP=0: everything on one
+    # stream).  In a CP step V derives from the group-summed rho, so the broadcast is ordered after the all-reduce.
     side = torch.cuda.Stream(device=dev, priority=-1) if seg is not None else None
     overlap_bcast = seg is not None and os.environ.get("CPB_BCAST_OVERLAP", "1") != "0"
 
@@ -429,19 +429,26 @@ def run_ours(args, rank, world, local):
         vpsi on the rank's block.  Returns the group-summed (ekin, rsum_g, rsum_r)."""
         ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
         if seg is not None:
-            seg.allreduce(0, nn, stream=stream)        # cp_grp_redist(rhoe), rhoofr_utils.mod.F90:457-461
             if overlap_bcast:
+                # all three exchanges go to the side stream, in the order of a CP step (V derives from the
+                # group-summed rho): cp_grp_redist(rhoe) (rhoofr_utils.mod.F90:457-461) -> V broadcast -> the
+                # group sum of the 2-3 scalars (SURVEY 8e).  vpsi is enqueued before the host waits for the
+                # scalars: its gather and x / y inverse passes need neither rho nor V and run under the
+                # exchanges, only the first z pass waits for V (cpb_plan_set_vpot_event).
                 done = torch.cuda.Event()
                 done.record(stream)
                 side.wait_event(done)
-                seg.bcast(nn, nn, src=0, stream=side)  # V(r) once per step
+                seg.allreduce(0, nn, stream=side)
+                seg.bcast(nn, nn, src=0, stream=side)
                 vready = torch.cuda.Event()
                 vready.record(side)
-                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)   # SURVEY 8e: the 2-3 doubles
                 plan.set_vpot_event(vready)
-            else:
-                seg.bcast(nn, nn, src=0, stream=stream)
-                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)
+                plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
+                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=side)   # waits for the side stream only
+                return ek, rg, rr
+            seg.allreduce(0, nn, stream=stream)
+            seg.bcast(nn, nn, src=0, stream=stream)
+            ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)
         elif world > 1:
             cdist.cp_grp_redist(rho)
             cdist.bcast_potential(v, src=0)
