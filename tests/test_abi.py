@@ -114,3 +114,71 @@ def test_fortran_interface_module_matches_header():
         f_args = [a.strip() for a in args.split(",") if a.strip()]
         assert cname in lib.SYMBOLS, cname
         assert [rename.get(a, a) for a in f_args] == c_params(cname), cname
+
+
+def _split_args(s):
+    """Top-level comma split of a Fortran actual-argument list."""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_fortran_shim_uses_declared_interfaces():
+    """integration/cpb200_shim.mod.F90 (the buildable drop-in: cpb_shim_rhoofr / cpb_shim_vpsi with the
+    reference's argument lists) cannot be compiled here either: check that every library call in it names
+    an interface cpb200_interfaces.mod.F90 declares and passes as many arguments as the C prototype has, and
+    that the two shim routines keep the reference's dummy-argument lists (rhoofr_utils.mod.F90:122,
+    vpsi_utils.mod.F90:120)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "cpb200.h")).read(), flags=re.S)
+    iface = open(os.path.join(ROOT, "integration", "cpb200_interfaces.mod.F90")).read()
+    src = open(os.path.join(ROOT, "integration", "cpb200_shim.mod.F90")).read()
+    src = "\n".join(l.split("!")[0] for l in src.split("\n"))   # drop comments
+    src = re.sub(r"&\s*\n\s*", "", src)                          # join continuation lines
+    declared = set(re.findall(r"BIND\(c,\s*name='(\w+)'\)", iface))
+    calls = []
+    for m in re.finditer(r"=\s*(cpb_\w+)\s*\(", src):
+        name, i, depth = m.group(1), m.end(), 1
+        j = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        calls.append((name, _split_args(src[i:j - 1])))
+    assert {c[0] for c in calls} >= {"cpb_plan_create", "cpb_rhoofr", "cpb_vpsi", "cpb_rhoofr_lsd", "cpb_vpsi_lsd"}
+    for name, args in calls:
+        assert name in declared and name in lib.SYMBOLS, name
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+        nparams = 0 if m.group(1).strip() in ("", "void") else len(m.group(1).split(","))
+        assert len(args) == nparams, (name, len(args), nparams)
+    assert re.search(r"SUBROUTINE cpb_shim_rhoofr\(c0,rhoe,psi,nstate,handled\)", src)
+    assert re.search(r"SUBROUTINE cpb_shim_vpsi\(c0,c2,f,vpot,psi,nstate,ikind,ispin,redist_c2,handled\)", src)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree")
+def test_guard_patch_applies_to_the_reference(tmp_path):
+    """integration/rhoofr_vpsi_guard.patch applies cleanly (patch -p1) to copies of the four reference files
+    it touches and inserts the two guards in front of the first executable statement of rhoofr / vpsi."""
+    import shutil
+    import subprocess
+    os.makedirs(tmp_path / "src")
+    for f in ("rhoofr_utils.mod.F90", "vpsi_utils.mod.F90", "cpmd.F90", "SOURCES"):
+        shutil.copy(os.path.join("/root/reference/src", f), tmp_path / "src" / f)
+    patch = os.path.join(ROOT, "integration", "rhoofr_vpsi_guard.patch")
+    out = subprocess.run(["patch", "-p1", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rho = open(tmp_path / "src" / "rhoofr_utils.mod.F90").read()
+    vps = open(tmp_path / "src" / "vpsi_utils.mod.F90").read()
+    assert rho.index("CALL cpb_shim_rhoofr(c0,rhoe,psi,nstate,cpb_handled)") < rho.index("CALL kin_energy(c0,nstate,rsum)")
+    assert vps.index("CALL cpb_shim_vpsi(c0,c2,f,vpot,psi,nstate,ikind,ispin,redist_c2,cpb_handled)") < \
+        vps.index("IF (group%nogrp.GT.1)CALL stopgm(procedureN")
+    assert "cpb200_shim.mod.F90" in open(tmp_path / "src" / "SOURCES").read()
