@@ -427,7 +427,13 @@ def run_ours(args, rank, world, local):
     def step_device():
         """rhoofr on the rank's block -> cp_grp_redist(rho) + the 3 group-partial scalars -> V broadcast ->
         vpsi on the rank's block.  Returns the group-summed (ekin, rsum_g, rsum_r)."""
-        ek, rg, rr = plan.rhoofr_dev(c0, f_block, rho, stream=stream)
+        # device-pointer calls with CPB_ASYNC only enqueue: the stream never drains between rhoofr and vpsi, the
+        # host picks up rhoofr's three sums (cpb_rhoofr_finish) while vpsi runs
+        sums = plan.rhoofr_dev(c0, f_block, rho, stream=stream, flags=lib.CPB_ASYNC)
+
+        def rho_sums():
+            return sums if sums is not None else plan.rhoofr_finish()   # None: enqueue-only call pending
+
         if seg is not None:
             if overlap_bcast:
                 # all three exchanges go to the side stream, in the order of a CP step (V derives from the
@@ -443,17 +449,21 @@ def run_ours(args, rank, world, local):
                 vready = torch.cuda.Event()
                 vready.record(side)
                 plan.set_vpot_event(vready)
-                plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
-                ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=side)   # waits for the side stream only
+                plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_ASYNC)
+                ek, rg, rr = seg.allreduce_scalars(list(rho_sums()), stream=side)   # waits for the side stream only
                 return ek, rg, rr
             seg.allreduce(0, nn, stream=stream)
             seg.bcast(nn, nn, src=0, stream=stream)
-            ek, rg, rr = seg.allreduce_scalars([ek, rg, rr], stream=stream)
+            ek, rg, rr = seg.allreduce_scalars(list(rho_sums()), stream=stream)
         elif world > 1:
+            ek, rg, rr = rho_sums()
             cdist.cp_grp_redist(rho)
             cdist.bcast_potential(v, src=0)
             ek, rg, rr = cdist.redist_scalars(ek, rg, rr, device=dev)
-        plan.vpsi_dev(c0, c2, f_block, v, stream=stream)
+        else:
+            plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_ASYNC)
+            return rho_sums()
+        plan.vpsi_dev(c0, c2, f_block, v, stream=stream, flags=lib.CPB_ASYNC)
         return ek, rg, rr
 
     def checks():

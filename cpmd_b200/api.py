@@ -286,7 +286,9 @@ class Plan:
     # -- device-pointer entry points (torch CUDA tensors) ----------------------------------
     def rhoofr_dev(self, c0, f, rhoe, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):
         """``cpb_rhoofr_dev``: c0 (nstate, ld) complex128 CUDA tensor, rhoe float64 CUDA tensor of
-        nnr1 elements (overwritten).  Returns (ekin, rsum_g, rsum_r) of the group's block."""
+        nnr1 elements (overwritten).  Returns (ekin, rsum_g, rsum_r) of the group's block; with
+        ``lib.CPB_ASYNC`` in ``flags`` the call only enqueues and returns None: :meth:`rhoofr_finish`
+        hands out the three sums."""
         nstate, ld = self._c0_args(c0, nstate)
         f = self._f_arg(f, nstate)
         if rhoe.numel() < self.nnr1:
@@ -296,6 +298,15 @@ class Plan:
                                     _ptr(rhoe), C.byref(ekin), C.byref(rg), C.byref(rr), flags,
                                     _stream_ptr(stream))
         self._check(rc)
+        if flags & _lib.CPB_ASYNC and self._L.cpb_rhoofr_pending(self._h):
+            return None
+        return ekin.value, rg.value, rr.value
+
+    def rhoofr_finish(self):
+        """``cpb_rhoofr_finish``: (ekin, rsum_g, rsum_r) of the pending ``CPB_ASYNC`` :meth:`rhoofr_dev` call;
+        waits for that call's partial sums only."""
+        ekin, rg, rr = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._L.cpb_rhoofr_finish(self._h, C.byref(ekin), C.byref(rg), C.byref(rr), None, None))
         return ekin.value, rg.value, rr.value
 
     def vpsi_dev(self, c0, c2, f, vpot, nstate=None, ngroups=1, my_group=0, flags=0, stream=None):

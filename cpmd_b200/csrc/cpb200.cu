@@ -172,6 +172,17 @@ struct cpb_plan {
   int *d_st1 = nullptr, *d_st2 = nullptr;
   double *d_ca = nullptr, *d_cb = nullptr;
   void* h_pairs = nullptr;  // pinned staging for the four arrays
+  rt::event_t ev_pairs = nullptr;  // recorded behind the staging buffer's copies (CPB_ASYNC calls return before them)
+  bool pairs_pending = false;
+  // CPB_ASYNC rhoofr: what cpb_rhoofr_finish needs once the partial sums have arrived in h_red
+  struct PendingRho {
+    bool active = false;
+    std::vector<double> f;
+    int first = 0, nblk = 0, ngroups = 1;
+    bool lsd = false;
+    unsigned flags = 0;
+    rt::event_t ev = nullptr;
+  } pending_rho;
   // reductions
   int red_cap = 0;
   double* d_red = nullptr;
@@ -233,6 +244,8 @@ void free_plan(cpb_plan* p) {
     rt::event_destroy(w.ev_rho);
   }
   rt::event_destroy(p->ev_fork);
+  rt::event_destroy(p->ev_pairs);
+  rt::event_destroy(p->pending_rho.ev);
   rt::dfree(p->T2keep);
   rt::dfree(p->d_st1);
   rt::dfree(p->d_st2);
@@ -296,6 +309,7 @@ void ensure_pairs(cpb_plan* p, int npairs) {
 
 void ensure_red(cpb_plan* p, int n) {
   if (n <= p->red_cap) return;
+  if (p->pending_rho.active) throw Error(-1, "a CPB_ASYNC rhoofr is pending on this plan: call cpb_rhoofr_finish first");
   rt::dfree(p->d_red);
   rt::hfree_pinned(p->h_red);
   p->d_red = (double*)rt::dmalloc((size_t)n * sizeof(double));
@@ -307,6 +321,10 @@ void ensure_red(cpb_plan* p, int n) {
 PairDev upload_pairs(cpb_plan* p, const std::vector<PairHost>& pairs, const std::vector<double>& ca,
                      const std::vector<double>& cb, cudaStream_t st) {
   const int np = (int)pairs.size();
+  if (p->pairs_pending) {  // an enqueue-only call may still be copying out of the staging buffer
+    rt::event_sync(p->ev_pairs);
+    p->pairs_pending = false;
+  }
   ensure_pairs(p, np);
   double* hca = (double*)p->h_pairs;
   double* hcb = hca + p->pair_cap;
@@ -323,6 +341,9 @@ PairDev upload_pairs(cpb_plan* p, const std::vector<PairHost>& pairs, const std:
     rt::h2d(p->d_st2, hs2, np * sizeof(int), st);
     rt::h2d(p->d_ca, hca, np * sizeof(double), st);
     rt::h2d(p->d_cb, hcb, np * sizeof(double), st);
+    if (!p->ev_pairs) p->ev_pairs = rt::event_create();
+    rt::event_record(p->ev_pairs, st);
+    p->pairs_pending = true;
   }
   PairDev pr;
   pr.st1 = p->d_st1;
@@ -1174,6 +1195,8 @@ static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nsta
   if (int e = check_common(p, c0_dev, ld_c0, nstate, f, ngroups, my_group)) return e;
   if (!rhoe_dev) return fail(CPB_ERR_INVALID, "null rhoe");
   if (nsup > nstate) return fail(CPB_ERR_INVALID, "nsup larger than nstate");
+  if (p->pending_rho.active)
+    return fail(CPB_ERR_INVALID, "a CPB_ASYNC rhoofr is pending on this plan: call cpb_rhoofr_finish first");
   try {
     rt::set_device(p->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1200,6 +1223,20 @@ static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nsta
     if (lsd) launch_lsd_sums(p, rhoe_dev, rhoe_dev + nnr1, nnr1, d_sums, ngroups == 1, st);  // :543-559
     else launch_sum(p, rhoe_dev, nnr1, d_sums, st);                                            // :607-619
     rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + 3 * kSumBlocks) * sizeof(double), st);
+    if ((flags & CPB_ASYNC) && !p->profiling) {
+      // enqueue-only: the partial sums are on their way to h_red; cpb_rhoofr_finish waits for them
+      cpb_plan::PendingRho& pr = p->pending_rho;
+      if (!pr.ev) pr.ev = rt::event_create();
+      rt::event_record(pr.ev, st);
+      pr.active = true;
+      pr.f.assign(f, f + nstate);
+      pr.first = first;
+      pr.nblk = nblk;
+      pr.ngroups = ngroups;
+      pr.lsd = lsd;
+      pr.flags = flags;
+      return CPB_OK;
+    }
     rt::sync(st);
     resolve_spans(p);
     double rg = 0, rr = 0;
@@ -1229,6 +1266,29 @@ int cpb_rhoofr_lsd_dev(cpb_plan* p, const void* c0_dev, long ld_c0, int nstate, 
   if (nsup < 0) return fail(CPB_ERR_INVALID, "negative nsup");
   return rhoofr_dev_impl(p, c0_dev, ld_c0, nstate, f, nsup, ngroups, my_group, rhoe_dev, ekin, rsum_g, rsum_r, csums,
                          csumsabs, flags, stream);
+}
+
+int cpb_rhoofr_pending(cpb_plan* p) { return (p && p->pending_rho.active) ? 1 : 0; }
+
+int cpb_rhoofr_finish(cpb_plan* p, double* ekin, double* rsum_g, double* rsum_r, double* csums, double* csumsabs) {
+  if (!p) return fail(CPB_ERR_INVALID, "null plan");
+  cpb_plan::PendingRho& pr = p->pending_rho;
+  if (!pr.active) return fail(CPB_ERR_INVALID, "no CPB_ASYNC rhoofr is pending on this plan");
+  try {
+    rt::set_device(p->device);
+    rt::event_sync(pr.ev);
+    pr.active = false;
+    rt::check_last("rhoofr kernels");
+    double rg = 0, rr = 0;
+    finish_rho_scalars(p, pr.f.data(), pr.first, pr.nblk, pr.lsd, ekin, &rg, &rr, csums, csumsabs);
+    if (rsum_g) *rsum_g = rg;
+    if (rsum_r) *rsum_r = rr;
+    if ((pr.flags & CPB_RHO_CHECK_CHARGE) && pr.ngroups == 1 && std::fabs(rr - rg) > 1.0e-6)
+      return fail(CPB_ERR_CHARGE, "TOTAL DENSITY SUMS ARE NOT EQUAL");  // rhoofr_utils.mod.F90:625-635
+    return CPB_OK;
+  } catch (const Error& e) {
+    return fail(e.code, e.what());
+  }
 }
 
 int cpb_lsd_finish_dev(cpb_plan* p, double* rhoe_dev, double* rsum_r, double* csums, double* csumsabs,
@@ -1266,6 +1326,7 @@ static int vpsi_dev_impl(cpb_plan* p, const void* c0_dev, void* c2_dev, long ld,
     run_vpsi(p, (const cplx*)c0_dev, (cplx*)c2_dev, ld, upload_pairs(p, pairs, fi, fip1, st), (int)pairs.size(),
              count_chan0(pairs), vpot_dev, vpot_dev + p->nnr1(),
              !(flags & CPB_VPSI_OVERWRITE), reuse ? p->T2keep : nullptr, st, nullptr);
+    if ((flags & CPB_ASYNC) && !p->profiling) return CPB_OK;  // enqueue-only
     rt::sync(st);
     resolve_spans(p);
     return CPB_OK;

@@ -27,6 +27,7 @@ CPB_C0_KEEP = 0x10
 CPB_C0_REUSE = 0x20
 CPB_PSI_KEEP = 0x40
 CPB_PSI_REUSE = 0x80
+CPB_ASYNC = 0x100
 CPB_DENSE_ACCUMULATE = 1
 CPB_PEER_HANDLE_BYTES = 64
 
@@ -134,6 +135,8 @@ SYMBOLS = {
                           C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint]),
     "cpb_plan_launch_count": (C.c_long, [C.c_void_p]),
     "cpb_plan_set_vpot_event": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cpb_rhoofr_finish": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 5),
+    "cpb_rhoofr_pending": (C.c_int, [C.c_void_p]),
     "cpb_plan_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_set_streams": (C.c_int, [C.c_void_p, C.c_int]),
     "cpb_plan_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]),

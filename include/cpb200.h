@@ -76,6 +76,13 @@ typedef enum {
  * (MD step: forces_driver.mod.F90:165 -> :224).  Silently ignored when the device has no room. */
 #define CPB_PSI_KEEP 0x40u
 #define CPB_PSI_REUSE 0x80u
+/* device-pointer entry points cpb_rhoofr[_lsd]_dev / cpb_vpsi[_lsd]_dev: only ENQUEUE the work on `stream` and
+ * return (like every CUDA library call; later work on the stream sees the results).  cpb_vpsi*_dev has nothing
+ * to hand back.  cpb_rhoofr*_dev leaves ekin / rsum_g / rsum_r (/ csums / csumsabs) untouched: fetch them with
+ * cpb_rhoofr_finish, which waits for the partial sums of that call only - work enqueued behind it (the group
+ * exchanges, the vpsi of the same step) keeps running.  One pending rhoofr per plan.  `f` is copied.  Ignored
+ * (the call synchronises as usual) while per-kernel profiling is on. */
+#define CPB_ASYNC 0x100u
 
 typedef struct {
   int nr[3];          /* mesh */
@@ -189,6 +196,13 @@ int cpb_vpsi_dev(cpb_plan* plan, const void* c0_dev, void* c2_dev, long ld, int 
  * gather and the x / y passes of that batch overlap the producer instead of queueing behind it.  Without
  * it the caller orders the whole call after the producer as usual.  NULL clears a pending hint. */
 int cpb_plan_set_vpot_event(cpb_plan* plan, void* event);
+
+/* Second half of a cpb_rhoofr_dev / cpb_rhoofr_lsd_dev call made with CPB_ASYNC: waits until that call's
+ * partial sums have reached the host and returns what the synchronous call returns (csums / csumsabs: LSD
+ * only, may be NULL).  CPB_RHO_CHECK_CHARGE of the call is honoured here. */
+int cpb_rhoofr_finish(cpb_plan* plan, double* ekin, double* rsum_g, double* rsum_r, double* csums, double* csumsabs);
+/* 1 while a CPB_ASYNC rhoofr waits for its cpb_rhoofr_finish (0 if the call synchronised after all: profiling on) */
+int cpb_rhoofr_pending(cpb_plan* plan);
 
 /* ---- dense transforms on the density cutoff and the local part of vofrho -------------------
  * (the step between rhoofr and vpsi.)  These run on a plan created by cpb_plan_create

@@ -764,3 +764,33 @@ def test_warp_x_kernels_match_block_kernels_and_oracle(dev, monkeypatch, n, nsta
     c2 = torch.full_like(c0, 3.0)
     pw.vpsi_dev(c0, c2, d["f"], v, flags=lib.CPB_VPSI_OVERWRITE)
     assert relmax(c2.cpu().numpy(), o.vpsi(geo, d["c0"], np.zeros_like(d["c0"]), d["f"], d["vpot"], 1.0)) < RTOL
+
+
+def test_async_device_entry_points(dev):
+    """CPB_ASYNC: cpb_rhoofr_dev / cpb_vpsi_dev only enqueue, cpb_rhoofr_finish hands out the sums; results are
+    bit-identical with the synchronous calls, a second rhoofr while one is pending is refused, and with
+    profiling on the flag is ignored (the call synchronises and returns the sums itself)."""
+    n, ns = 48, 9
+    d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    plan = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    v = torch.from_numpy(d["vpot"]).to(dev)
+    rho_s = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    sums_s = plan.rhoofr_dev(c0, d["f"], rho_s)
+    c2_s = 0.5 * c0
+    plan.vpsi_dev(c0, c2_s, d["f"], v)
+    rho_a = torch.full_like(rho_s, 7.0)
+    c2_a = 0.5 * c0
+    assert plan.rhoofr_dev(c0, d["f"], rho_a, flags=lib.CPB_ASYNC) is None
+    with pytest.raises(Exception):
+        plan.rhoofr_dev(c0, d["f"], rho_a, flags=lib.CPB_ASYNC)        # one pending rhoofr per plan
+    plan.vpsi_dev(c0, c2_a, d["f"], v, flags=lib.CPB_ASYNC)             # enqueued behind it, no host sync
+    sums_a = plan.rhoofr_finish()
+    torch.cuda.synchronize()
+    assert sums_a == sums_s
+    assert torch.equal(rho_a, rho_s) and torch.equal(c2_a, c2_s)
+    with pytest.raises(Exception):
+        plan.rhoofr_finish()                                            # nothing pending any more
+    plan.set_profiling(True)
+    assert plan.rhoofr_dev(c0, d["f"], rho_a, flags=lib.CPB_ASYNC) == sums_s
+    plan.set_profiling(False)
