@@ -133,11 +133,15 @@ void x_fwd_m(cudaStream_t st, const cplx* T1, const cplx* c0, cplx* c2, long ldc
 }
 
 constexpr size_t kSmemYZ2 = 2 * kSmemYZ;  // double-buffered exchange
+// exchange buffers of the staged kernels: the tuning macro, unless two buffers would leave one block per SM (YZXB)
+constexpr int kXBy = (CPB_YINV_XB == 2) ? YZXB<R1, R2, B>::v : CPB_YINV_XB;
+constexpr int kXBz = (CPB_ZRHO_XB == 2) ? YZXB<R1, R2, B>::v : CPB_ZRHO_XB;
+constexpr int kXBv = YZXB<R1, R2, B>::v;
 
 template <bool HALF>
 void y_inv_t(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npair, int xt0, int nxc, int ppg) {
-  auto k = k_y_inv<R1, R2, B, HALF, CPB_YINV_XB>;
-  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nyb * B, CPB_YINV_XB);
+  auto k = k_y_inv<R1, R2, B, HALF, kXBy>;
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nyb * B, kXBy);
   allow_smem(k, smem);
   CPB_LAUNCH_PDL(1, k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
              dim3(B * RM), smem, st, T1, T2, pd, xt0, npair, ppg);
@@ -164,8 +168,8 @@ void y_fwd(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npa
 template <bool HALF>
 void z_rho_t(cudaStream_t st, const cplx* T2, double* rho, const PlanDev& pd, const PairDev& pr, int npair,
              int xt0, int nxc) {
-  auto k = k_z_rho<R1, R2, B, HALF, CPB_ZRHO_XB>;
-  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B, CPB_ZRHO_XB);
+  auto k = k_z_rho<R1, R2, B, HALF, kXBz>;
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B, kXBz);
   allow_smem(k, smem);
   CPB_LAUNCH_PDL(2, k, dim3(nxc, pd.n2), dim3(B * RM), smem, st, T2, rho, pd, pr, npair, xt0);
 }
@@ -178,8 +182,8 @@ void z_rho(cudaStream_t st, const cplx* T2, double* rho, const PlanDev& pd, cons
 template <bool HALF>
 void z_vpsi_t(cudaStream_t st, cplx* T2, const double* vpot, const PlanDev& pd, int npair, int xt0, int nxc,
               int ppg) {
-  auto k = k_z_vpsi<R1, R2, B, HALF>;
-  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B);
+  auto k = k_z_vpsi<R1, R2, B, HALF, kXBv>;
+  const size_t smem = YZCfg<R1, R2, B>::smem(pd.nzb * B, kXBv);
   allow_smem(k, smem);
   CPB_LAUNCH_PDL(3, k, dim3(nxc, pd.n2, (npair + ppg - 1) / ppg), dim3(B * RM), smem, st, T2, vpot, pd, xt0, npair, ppg);
 }

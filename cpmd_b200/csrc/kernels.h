@@ -828,6 +828,16 @@ struct YZCfg {
   }
 };
 
+// Exchange buffers of the staged y/z kernels: two (one block barrier per transform) unless that leaves room for
+// only one block per SM (lengths from 288 on: 2 x 16 N B bytes of exchange + the TMA ring exceed half an SM's
+// shared memory); then one buffer and one more barrier per transform, and two blocks per SM again.  The tile is
+// taken as the dual = 4 band (half the axis).
+template <int R1, int R2, int B>
+struct YZXB {
+  static constexpr size_t two = YZCfg<R1, R2, B>::smem((R1 * R2 / 2 + 1) * B, 2);
+  static constexpr int v = (2 * (two + 1024) <= (size_t)228 * 1024) ? 2 : 1;
+};
+
 // ---------------------------------------------------------------------------------------------
 // y pass, inverse.  Block = (x tile of the chunk, z plane of the band, group of pairs).  Reads the
 // rays of the plane (zero outside [ylo,yhi]: unpack_x2y's zero fill, fftutil_utils.mod.F90:413-457),
@@ -1084,14 +1094,16 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
 // thread stores exactly the elements it loaded.  V tile lives in registers over the pair loop.
 // grid = (x tiles of the chunk, n2, pair groups)
 // ---------------------------------------------------------------------------------------------
-template <int R1, int R2, int B, bool HALF>
+// XB = 2: separate exchange buffers for the inverse and the forward transform (two block barriers per pair);
+// XB = 1: one buffer, two more barriers (the large lengths, see YZXB).
+template <int R1, int R2, int B, bool HALF, int XB = 2>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     k_z_vpsi(cplx* T2, const double* CPB_RESTRICT vpot, PlanDev pd, int xt0, int npair, int ppg) {
   using C = YZCfg<R1, R2, B>;
   constexpr int N = C::N, RM = C::RM, NT = C::NT;
   using KR = KRange<R1, HALF>;
   CPB_DYN_SMEM(cplx, S);
-  cplx* TW = S + 2 * N * B;
+  cplx* TW = S + XB * N * B;
   cplx* ST = TW + N;
   const int tile_elems = pd.nzb * B;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ST + (size_t)kStages * tile_elems);
@@ -1126,8 +1138,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
       bulk_g2s(ST + (size_t)s * tile_elems, tile + (size_t)(p0 + s) * pstride, tile_bytes, &bar[s]);
     }
   }
-  cplx* Sa = S + b;            // exchange buffer of the inverse transform
-  cplx* Sf = S + N * B + b;    // exchange buffer of the forward transform
+  cplx* Sa = S + b;                             // exchange buffer of the inverse transform
+  cplx* Sf = S + (XB == 2 ? N * B : 0) + b;     // exchange buffer of the forward transform
   int rA = r;  // role in the band-side radix passes (rotates by one warp per pair)
   for (int pair = p0; pair < p1; ++pair) {
     const int it = pair - p0;
@@ -1152,16 +1164,17 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
       mbar_expect_tx(&bar[st], tile_bytes);
       bulk_g2s(ST + (size_t)st * tile_elems, tile + (size_t)(pair + kStages) * pstride, tile_bytes, &bar[st]);
     }
+    cplx u[R2];
     if (r < R1) {
-      cplx u[R2];
       pass_b<R1, R2, true>(u, r, Sa, B);
       static_for<0, R2>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
         u[q].x *= vv[q];
         u[q].y *= vv[q];
       });
-      pass_a<R2, R1, false, true>(u, r, TW, Sf, B);
     }
+    if constexpr (XB == 1) __syncthreads();  // everybody has read the single buffer before it is rewritten
+    if (r < R1) pass_a<R2, R1, false, true>(u, r, TW, Sf, B);
     __syncthreads();
     if (rA < R2) {
       cplx w[R1];
@@ -1173,6 +1186,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
         if (zr >= 0 && zr < nzb) d[zr * B] = w[k];
       });
     }
+    if constexpr (XB == 1) __syncthreads();  // ... and before the next pair's inverse pass writes it
     if constexpr (C::ROT) {
       rA += C::RPW;
       if (rA >= RM) rA -= RM;
