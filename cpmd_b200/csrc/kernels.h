@@ -161,6 +161,43 @@ CPB_D void pass_b(cplx (&u)[RB], int p, const cplx* Sb, int LD) {
   dft<RB, INV>(u);
 }
 
+// Variants for kernels whose second-pass role is fixed over the pair loop (the z kernels): the first pass stores
+// its outputs untwiddled, the second pass multiplies by the twiddles w^(a p) of its role p, which it holds in
+// registers for the whole loop (tb[a], a >= 1) - no twiddle load inside the loop, and the multiplications move
+// from the pass that occupies RB of the max(RA,RB) role rows to the one that occupies RA.
+template <int RA, int RB, bool INV, int LO, int HI>
+CPB_D void pass_a_raw(cplx (&v)[RA], int a, cplx* Sb, int LD) {
+  dft_in<RA, INV, LO, HI>(v);
+  static_for<0, RA>([&](auto pp) {
+    constexpr int p = decltype(pp)::value;
+    Sb[(p * RB + a) * LD] = v[p];
+  });
+}
+// tb[a] = exp(+2 pi i a p / N); INV: multiply by tb, else by conj(tb)
+template <int RA, int RB, bool INV>
+CPB_D void pass_b_tw(cplx (&u)[RB], int p, const cplx* Sb, int LD, const cplx (&tb)[RB]) {
+  static_for<0, RB>([&](auto aa) {
+    constexpr int a = decltype(aa)::value;
+    u[a] = Sb[(p * RB + a) * LD];
+    if constexpr (a != 0) u[a] = INV ? cmul(u[a], tb[a]) : cmulc(u[a], tb[a]);
+  });
+  dft<RB, INV>(u);
+}
+// forward first pass of role a with the same register twiddles: dft, times conj(tb[p]), store
+template <int RA, int RB>
+CPB_D void pass_a_fwd_tw(cplx (&v)[RA], int a, cplx* Sb, int LD, const cplx (&tb)[RA]) {
+  dft<RA, false>(v);
+  static_for<0, RA>([&](auto pp) {
+    constexpr int p = decltype(pp)::value;
+    cplx o = v[p];
+    if constexpr (p != 0) o = cmulc(o, tb[p]);
+    Sb[(p * RB + a) * LD] = o;
+  });
+}
+#ifndef CPB_Z_TWREG
+#define CPB_Z_TWREG 1  // z kernels: twiddles of the fixed real-space-side role in registers (0: shared-memory table)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // x passes.  Positions along a ray are addressed like the reference's compressed ray storage
 // psi(kr1s, msrays) (fftprp_utils.mod.F90:269-285) restricted to the x band that holds
@@ -1024,7 +1061,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
     for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
+#if CPB_Z_TWREG
+  cplx tb[R2];  // twiddles of my real-space-side role r
+  static_for<0, R2>([&](auto aa) {
+    constexpr int a = decltype(aa)::value;
+    tb[a] = (r < R1) ? __ldg(&pd.tw3[(a * r) % N]) : mk(1.0, 0.0);
+  });
+#else
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw3[i];
+#endif
   pdl_wait();  // T2 and rho come from preceding kernels
   // the accumulators start from rho itself: the read-modify-write's read overlaps the first tile
   double acc[R2];
@@ -1057,7 +1102,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
           v[k] = mk(0.0, 0.0);
         }
       });
+#if CPB_Z_TWREG
+      pass_a_raw<R1, R2, true, KR::lo, KR::hi>(v, rA, Sb, B);
+#else
       pass_a_in<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, Sb, B);
+#endif
     }
     __syncthreads();
     if (tid == 0 && pair + kStages < npair) {
@@ -1066,7 +1115,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
     }
     if (r < R1) {
       cplx u[R2];
+#if CPB_Z_TWREG
+      pass_b_tw<R1, R2, true>(u, r, Sb, B, tb);
+#else
       pass_b<R1, R2, true>(u, r, Sb, B);
+#endif
       static_for<0, R2>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
         acc[q] += ca * (u[q].x * u[q].x) + cb * (u[q].y * u[q].y);
@@ -1124,7 +1177,15 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
+#if CPB_Z_TWREG
+  cplx tb[R2];  // twiddles of my real-space-side role r
+  static_for<0, R2>([&](auto aa) {
+    constexpr int a = decltype(aa)::value;
+    tb[a] = (r < R1) ? __ldg(&pd.tw3[(a * r) % N]) : mk(1.0, 0.0);
+  });
+#else
   for (int i = tid; i < N; i += NT) TW[i] = pd.tw3[i];
+#endif
   pdl_wait();  // T2 (and possibly V) come from preceding kernels
   double vv[R2];
   static_for<0, R2>([&](auto qq) {
@@ -1157,7 +1218,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
           v[k] = mk(0.0, 0.0);
         }
       });
+#if CPB_Z_TWREG
+      pass_a_raw<R1, R2, true, KR::lo, KR::hi>(v, rA, Sa, B);
+#else
       pass_a_in<R1, R2, true, KR::lo, KR::hi, true>(v, rA, TW, Sa, B);
+#endif
     }
     __syncthreads();
     if (tid == 0 && pair + kStages < p1) {
@@ -1166,7 +1231,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     }
     cplx u[R2];
     if (r < R1) {
+#if CPB_Z_TWREG
+      pass_b_tw<R1, R2, true>(u, r, Sa, B, tb);
+#else
       pass_b<R1, R2, true>(u, r, Sa, B);
+#endif
       static_for<0, R2>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
         u[q].x *= vv[q];
@@ -1174,7 +1243,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
       });
     }
     if constexpr (XB == 1) __syncthreads();  // everybody has read the single buffer before it is rewritten
+#if CPB_Z_TWREG
+    if (r < R1) pass_a_fwd_tw<R2, R1>(u, r, Sf, B, tb);
+#else
     if (r < R1) pass_a<R2, R1, false, true>(u, r, TW, Sf, B);
+#endif
     __syncthreads();
     if (rA < R2) {
       cplx w[R1];
