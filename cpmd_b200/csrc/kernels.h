@@ -699,7 +699,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   const bool actA = rA < R2;
   const bool okB = slotB < SL && sb.valid;
   const int spA = sa.self ? slotA : (slotA + H) % SL;
+  #if defined(CPB_DEBUG_KNOBS) && (CPB_DEBUG_KNOBS & 16)
+  const size_t t1_pair = 0;  // experiment: every pair reads the same (L2-resident) T1 region
+#else
   const size_t t1_pair = (size_t)pd.nxt * pd.nrays * B;
+#endif
   const double sc = pd.inv_n;
   uint32_t tab[KR::cnt];
   double g2v[NPOS];
@@ -740,11 +744,16 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
         constexpr int j = k - KR::lo;
         if (tab[j] != kNoPW && !(tab[j] & kNegPW)) {
           const int o = (k - C0) * NA + tidA;
-          cp_async16(&CS[0 * NPOS * NA + o], a1 + tab[j]);
-          if (s2 >= 0) cp_async16(&CS[1 * NPOS * NA + o], a2 + tab[j]);
+#if defined(CPB_DEBUG_KNOBS) && (CPB_DEBUG_KNOBS & 4)
+          const uint32_t ig = tab[j] & 0x3ffu;  // experiment: the coefficient gathers read a 16 KB window
+#else
+          const uint32_t ig = tab[j];
+#endif
+          cp_async16(&CS[0 * NPOS * NA + o], a1 + ig);
+          if (s2 >= 0) cp_async16(&CS[1 * NPOS * NA + o], a2 + ig);
           if constexpr (ACC) {
-            cp_async16(&CS[2 * NPOS * NA + o], o1 + tab[j]);
-            if (s2 >= 0) cp_async16(&CS[3 * NPOS * NA + o], o2 + tab[j]);
+            cp_async16(&CS[2 * NPOS * NA + o], o1 + ig);
+            if (s2 >= 0) cp_async16(&CS[3 * NPOS * NA + o], o2 + ig);
           }
         }
       });
@@ -785,7 +794,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
       static_for<C0, KR::hi>([&](auto tt) {
         constexpr int t = decltype(tt)::value;
         constexpr int j = t - KR::lo;
+#if defined(CPB_DEBUG_KNOBS) && (CPB_DEBUG_KNOBS & 8)
+        const uint32_t ig = (tab[j] == kNoPW || (tab[j] & kNegPW)) ? tab[j] : (tab[j] & 0x3ffu);  // experiment: c2 stores into a 16 KB window
+#else
         const uint32_t ig = tab[j];
+#endif
         if (ig != kNoPW && !(ig & kNegPW)) {
           const int o = (t - C0) * NA + tidA;
           const cplx psin = up[t - C0];
