@@ -111,6 +111,8 @@ struct cpb_plan {
   double tpiba2 = 0, omega = 0;
   int device = 0;
   int max_batch = 32;
+  int host_batch = 8;      // pairs per batch of the host-pointer entry points (finer copy / compute pipeline)
+  int batch_override = 0;  // > 0: batch size of the call in progress
   bool auto_batch = false;  // max_batch_pairs <= 0: sized from the work space of one pair once the ray table is known
   int nxt = 0;       // x tiles of B columns
   int chunk_xt = 1;  // x tiles per y/z chunk (T2 holds one chunk of the batch)
@@ -621,8 +623,9 @@ struct BatchSpan {
 };
 std::vector<BatchSpan> make_batches(const cpb_plan* p, int np, int n0) {
   std::vector<BatchSpan> out;
-  for (int off = 0; off < n0; off += p->max_batch) out.push_back({off, std::min(p->max_batch, n0 - off), 0});
-  for (int off = n0; off < np; off += p->max_batch) out.push_back({off, std::min(p->max_batch, np - off), 1});
+  const int mb = p->batch_override > 0 ? std::min(p->batch_override, p->max_batch) : p->max_batch;
+  for (int off = 0; off < n0; off += mb) out.push_back({off, std::min(mb, n0 - off), 0});
+  for (int off = n0; off < np; off += mb) out.push_back({off, std::min(mb, np - off), 1});
   return out;
 }
 
@@ -1039,6 +1042,7 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
+    if (const char* e = std::getenv("CPB_HOST_BATCH")) p->host_batch = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("CPB_STREAMS")) p->nws = std::max(1, std::min((int)cpb_plan::kNumWS, std::atoi(e)));
     for (int i = 0; i < p->nws; ++i) {
       cpb_plan::WorkSpace& w = p->ws[i];
