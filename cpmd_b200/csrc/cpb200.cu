@@ -1042,6 +1042,8 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     const size_t gb = (size_t)p->x_sub * p->g_pair * sizeof(cplx);
     const size_t t1 = (size_t)p->max_batch * p->nxt * nrays * Bx * sizeof(cplx);
     const size_t t2 = (size_t)p->max_batch * p->chunk_xt * n2 * nzb * Bx * sizeof(cplx);
+    // host-pointer calls: batches of at least 8 pairs and about 24 MB of coefficients (16 ngw bytes per state)
+    p->host_batch = std::max(8, (int)std::ceil(24.0e6 / (32.0 * std::max(p->ngw, 1))));
     if (const char* e = std::getenv("CPB_HOST_BATCH")) p->host_batch = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("CPB_STREAMS")) p->nws = std::max(1, std::min((int)cpb_plan::kNumWS, std::atoi(e)));
     for (int i = 0; i < p->nws; ++i) {

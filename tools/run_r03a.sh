@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r03a_pytest_gpu.log 2>&1; tail -3 gpurun_out/r03a_pytest_gpu.log
+timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/r03a_bench.json 2> gpurun_out/r03a_bench.err; tail -c 300 gpurun_out/r03a_bench.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r03a_bench.json'))
+print(d['ms_per_step'], d['value'], 'e2e', d['e2e']['ms_per_step'], d['e2e']['value'], 'ovw', d['e2e_overwrite']['ms_per_step'], d['roofline']['frac'], d['roofline']['step_frac'], d['checks']['all_ok'], d['clocks'])
+print(d['roofline']['kernel_ms_per_step'])
+for s in d['sweep']: print(s['mesh'], s['states'], s.get('pairs_per_batch'), round(s['ms_per_step'],3), round(s['step_frac'],3))
+print(d['cpu_baseline']['value'], d['reference_gpu']['value'], d['gpu_launches'])
+P
