@@ -5,25 +5,30 @@ only by ``tests/``, by ``__graft_entry__.smoke()`` and by the ``cpu_baseline`` /
 reference`` legs of ``bench.py``, and always as the *checker*, never as the thing that is shipped
 or measured as the GPU path.
 
-PARITY PARTLY PINNED BY REFERENCE CODE.  The reference tree (/root/reference, CPMD 4.3) ships no golden
-vectors, known-answer tests or fixtures for this path, and as a whole it cannot be compiled in the
-authoring container (Fortran 2008 + FFTW + MPI; no Fortran compiler is installed).  One part of the
-path does compile from its own source file: the helper kernels of the reference's cuFFT code path,
-src/cuuser_utils_kernels.cu (set_psi_1/2_states_g, build_density_sum, the pointwise V*psi, phasen,
-putz/getz via MatMov/Zeroing, pack/unpack x2y/y2x).  oracle/Makefile compiles that file for the host
-from where it lies (nothing copied; CPU stand-ins for the few CUDA names in oracle/ref_shim/) into
-oracle/_ref/libcuuser_ref.so, and tests/test_oracle_ref.py (a) compares this file's functions with
-those kernels one by one and (b) assembles fftnew's staged sparse inverse and forward transforms from
-the reference's data-movement kernels plus 1-D DFTs and checks them against the dense transforms used
-below.  That pins the packing rule, the nzhs/indzs and msp index maps as the reference consumes them,
-the z-band insertion, phasen and the density / V*psi formulas.  What remains a restatement, function
-by function with the reference file:line it follows (paths relative to /root/reference/src): the 1-D
-DFT itself (its sign/scale convention is the one mltfft_cuda states in code: isign = +1 -> CUFFT_FORWARD,
--1 -> CUFFT_INVERSE, then zdscal(scale), mltfft_utils.mod.F90:636-646), the loop structure of vpsi / rhoofr (pairing, occupation
-rules, unpacking at +-G, kinetic term), ppener, the k-point and tau variants.  Those are pinned by the
-known-answer tests derived from the reference's own formulas (tests/test_oracle.py) and by an
-independent second restatement (oracle/staged_oracle.c, which follows ``fftnew``'s staged sparse
-pipeline instead of a dense 3-D FFT).
+PARITY PINNED BY REFERENCE CODE (three ways; what is left unpinned is listed at the end).  The reference tree
+(/root/reference, CPMD 4.3) ships no golden vectors, known-answer tests or fixtures for this path, and as a whole it
+cannot be compiled in the authoring container (Fortran 2008 + FFTW + MPI; no Fortran compiler is installed).
+(1) The helper kernels of the reference's cuFFT code path, src/cuuser_utils_kernels.cu (set_psi_1/2_states_g,
+build_density_sum, the pointwise V*psi, phasen, putz/getz via MatMov/Zeroing, pack/unpack x2y/y2x), compile from
+their own file: oracle/Makefile builds them for the host from where they lie (nothing copied; CPU stand-ins for
+the few CUDA names in oracle/ref_shim/) into oracle/_ref/libcuuser_ref.so, and tests/test_oracle_ref.py (a)
+compares this file's functions with those kernels one by one and (b) assembles fftnew's staged sparse inverse and
+forward transforms from the reference's data-movement kernels plus 1-D DFTs and checks them against the dense
+transforms used below.  That pins the packing rule, the nzhs/indzs and msp index maps as the reference consumes
+them, the z-band insertion, phasen and the density / V*psi formulas.  (2) The same sources plus cuuser_utils.cu
+compile with nvcc: oracle/ref_gpu_driver.cu runs them with cuFFT plans laid out like cp_cufft_utils and the stage
+order of fftcu_methods on the GPU (tests/test_gpu_reference_arm.py compares the library with it).  (3) The parts
+that are plain Fortran loops - the pairing loops, the occupation rules, the +-G unpack with the kinetic term and the
+-f/2 scale, the density coefficients and accumulation, kin_energy, dotp, the LSD post-processing - are EXECUTED
+from the reference's own statements: oracle/fsnip.py reads the cited line ranges of vpsi_utils / rhoofr_utils /
+density_utils / kin_energy_utils / dotp_utils / part_1d from /root/reference/src and runs them statement by
+statement on NumPy data; tests/test_fsnip_pin.py compares this file with them (live, where the tree exists) and
+with the fixtures they produced (tests/golden/fsnip, tools/make_golden_fsnip.py), which the staged C oracle, the
+simulator build of the kernels and the GPU tests are checked against too.
+Still a restatement (pinned by known-answer tests derived from the reference's formulas, tests/test_oracle.py, and
+by the independent second restatement oracle/staged_oracle.c): the 1-D DFT itself (its sign/scale convention is
+the one mltfft_cuda states in code: isign = +1 -> CUFFT_FORWARD, -1 -> CUFFT_INVERSE, then zdscal(scale),
+mltfft_utils.mod.F90:636-646 - and the cuFFT run of (2) confirms it), ppener, the k-point, tau and hfx variants.
 
 All "Fortran" indices kept in arrays here are 1-based exactly like the reference's (``inyh``,
 ``nzhs``, ``indzs``); they are converted at the point of use.

@@ -96,3 +96,14 @@ def load_golden_tau(path):
     d["nsup"] = int(d["nsup"])
     d["nr"] = tuple(int(v) for v in d["nr"])
     return d
+
+
+def golden_fsnip_cases():
+    """Fixtures computed by the reference's own Fortran statements (tools/make_golden_fsnip.py, oracle/fsnip.py)."""
+    return sorted(glob.glob(os.path.join(GOLDEN, "fsnip", "*.npz")))
+
+
+def load_golden_fsnip(path):
+    d = load_golden(path)
+    d["tksham"] = bool(d["tksham"])
+    return d

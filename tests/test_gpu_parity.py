@@ -794,3 +794,26 @@ def test_async_device_entry_points(dev):
     plan.set_profiling(True)
     assert plan.rhoofr_dev(c0, d["f"], rho_a, flags=lib.CPB_ASYNC) == sums_s
     plan.set_profiling(False)
+
+
+from helpers import golden_fsnip_cases, load_golden_fsnip  # noqa: E402
+
+
+@pytest.mark.parametrize("path", golden_fsnip_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_reference_statement_fixtures(dev, path):
+    """tests/golden/fsnip: rho, ekin / rsum and C2 computed by the reference's own Fortran statements
+    (oracle/fsnip.py executing the cited line ranges of rhoofr_utils / vpsi_utils / density_utils / kin_energy_utils /
+    dotp_utils / part_1d); the device entry points must reproduce them."""
+    d = load_golden_fsnip(path)
+    plan = Plan(d["nr"], d["inyh"], d["hg"], d["tpiba2"], d["omega"], max_batch=2)
+    c0 = torch.from_numpy(d["c0"]).to(dev)
+    v = torch.from_numpy(d["vpot"]).to(dev)
+    rho = torch.empty(plan.nnr1, dtype=torch.float64, device=dev)
+    ekin, rg, rr = plan.rhoofr_dev(c0, d["f"], rho, ngroups=d["ngroups"], my_group=d["group"])
+    assert relmax(rho.cpu().numpy(), d["rhoe"]) < RTOL and abs(rr - d["rsum_r"]) < ETOL
+    if d["ngroups"] == 1:
+        assert abs(ekin - d["ekin"]) < ETOL and abs(rg - d["rsum_g"]) < ETOL
+    c2 = torch.from_numpy(d["c2_in"]).to(dev)
+    plan.vpsi_dev(c0, c2, d["f"], v, ngroups=d["ngroups"], my_group=d["group"],
+                  flags=lib.CPB_VPSI_TKSHAM if d["tksham"] else 0)
+    assert relmax(c2.cpu().numpy(), d["c2_out"]) < RTOL
