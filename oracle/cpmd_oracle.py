@@ -19,7 +19,9 @@ them, the z-band insertion, phasen and the density / V*psi formulas.  (2) The sa
 compile with nvcc: oracle/ref_gpu_driver.cu runs them with cuFFT plans laid out like cp_cufft_utils and the stage
 order of fftcu_methods on the GPU (tests/test_gpu_reference_arm.py compares the library with it).  (3) The parts
 that are plain Fortran loops - the pairing loops, the occupation rules, the +-G unpack with the kinetic term and the
--f/2 scale, the density coefficients and accumulation, kin_energy, dotp, the LSD post-processing - are EXECUTED
+-f/2 scale, the density coefficients and accumulation, kin_energy, dotp, the LSD branches and post-processing,
+rhoofr_c's k-point loop and the k-point unpack, tauofr / vtaupsi (dpsisc, tauadd, taupot, ftauadd), ppener, hfxab /
+hfxaa - are EXECUTED
 from the reference's own statements: oracle/fsnip.py reads the cited line ranges of vpsi_utils / rhoofr_utils /
 density_utils / kin_energy_utils / dotp_utils / part_1d from /root/reference/src and runs them statement by
 statement on NumPy data; tests/test_fsnip_pin.py compares this file with them (live, where the tree exists) and
@@ -28,7 +30,7 @@ simulator build of the kernels and the GPU tests are checked against too.
 Still a restatement (pinned by known-answer tests derived from the reference's formulas, tests/test_oracle.py, and
 by the independent second restatement oracle/staged_oracle.c): the 1-D DFT itself (its sign/scale convention is
 the one mltfft_cuda states in code: isign = +1 -> CUFFT_FORWARD, -1 -> CUFFT_INVERSE, then zdscal(scale),
-mltfft_utils.mod.F90:636-646 - and the cuFFT run of (2) confirms it), ppener, the k-point, tau and hfx variants.
+mltfft_utils.mod.F90:636-646 - and the cuFFT run of (2) confirms it) and hfx_old's outer pair loop.
 
 All "Fortran" indices kept in arrays here are 1-based exactly like the reference's (``inyh``,
 ``nzhs``, ``indzs``); they are converted at the point of use.

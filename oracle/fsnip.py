@@ -66,13 +66,16 @@ def ns(**kw):
 
 
 def _ddot_seq(n, x, kx, y, ky):
-    """``ddot(n, x(kx), 1, y(ky), 1)`` with COMPLEX arrays passed by sequence association: the dot product of the
-    n REAL words that start at element kx / ky."""
-    xr = np.ascontiguousarray(x.a).view(np.float64)
-    yr = np.ascontiguousarray(y.a).view(np.float64)
-    ox, oy = 2 * (int(kx) - 1), 2 * (int(ky) - 1)
+    """``ddot(n, x(kx...), 1, y(ky...), 1)`` with COMPLEX arrays passed by sequence association: the dot product of
+    the n REAL words that start at element x(kx...) / y(ky...) in Fortran (column-major) memory order."""
+    def words(arr, k):
+        a = np.asfortranarray(arr.a)
+        k = k if isinstance(k, tuple) else (k,)
+        off = int(np.ravel_multi_index(tuple(int(i) - 1 for i in k), a.shape, order="F"))
+        flat = a.reshape(-1, order="F")
+        return flat.view(np.float64)[2 * off:] if np.iscomplexobj(flat) else flat[off:]
     n = int(n)
-    return float(np.dot(xr[ox:ox + n], yr[oy:oy + n]))
+    return float(np.dot(words(x, kx)[:n], words(y, ky)[:n]))
 
 
 _BUILTINS = {
@@ -146,15 +149,21 @@ _OPS = [(r"\.EQ\.", "=="), (r"\.NE\.", "!="), (r"\.GT\.", ">"), (r"\.GE\.", ">="
         (r"\.AND\.", " and "), (r"\.OR\.", " or "), (r"\.NOT\.", " not "), (r"\.TRUE\.", "True"), (r"\.FALSE\.", "False")]
 
 
+_PYKW = re.compile(r"\b(is|in|as|def|del|from|global|lambda|pass|try|with|yield|class|for|while|import)\b")
+
+
 def _expr(e):
+    e = _PYKW.sub(lambda m: m.group(1) + "_", e)                        # Fortran names that are Python keywords
     e = re.sub(r"(\d+\.?\d*(?:[eEdD][+-]?\d+)?)_real_8", lambda m: m.group(1).replace("d", "e").replace("D", "e"), e)
     e = re.sub(r"(\d)\.(?=[^\d\w]|$)", r"\1.0", e)                      # "1." -> "1.0"
     for pat, rep in _OPS:
         e = re.sub(pat, rep, e, flags=re.I)
     e = e.replace("%", ".")
+    # complex literal (re,im): a parenthesised pair of numbers that is not an argument list
+    e = re.sub(r"(?<![\w)])\(\s*([-+]?\d[\d.]*(?:[eE][-+]?\d+)?)\s*,\s*([-+]?\d[\d.]*(?:[eE][-+]?\d+)?)\s*\)", r"complex(\1,\2)", e)
     e = re.sub(r"\bkind\s*=\s*real_8", "kind=None", e, flags=re.I)
     # ddot(n, a(k), 1, b(k), 1): sequence association of complex arrays -> ddot_seq(n, a, k, b, k)
-    e = re.sub(r"\bddot\(\s*([^,]+),\s*(\w+)\(([^)]+)\)\s*,\s*1\s*,\s*(\w+)\(([^)]+)\)\s*,\s*1\s*\)", r"ddot_seq(\1,\2,\3,\4,\5)", e)
+    e = re.sub(r"\bddot\(\s*([^,]+),\s*(\w+)\(([^)]+)\)\s*,\s*1\s*,\s*(\w+)\(([^)]+)\)\s*,\s*1\s*\)", r"ddot_seq(\1,\2,(\3,),\4,(\5,))", e)
     # a bare ':' subscript -> slice(None)
     e = re.sub(r"(?<=[(,])\s*:\s*(?=[,)])", "slice(None)", e)
     return e
@@ -216,7 +225,7 @@ def translate(stmts):
             m = re.match(r"^DO\s+(\w+)\s*=\s*(.*)$", s, flags=re.I)
             parts = [_expr(x) for x in _split_top(m.group(2))]
             step = parts[2] if len(parts) > 2 else "1"
-            py.append(f"{pad}for {m.group(1)} in range(int({parts[0]}), int({parts[1]}) + 1, int({step})):")
+            py.append(f"{pad}for {_expr(m.group(1))} in range(int({parts[0]}), int({parts[1]}) + 1, int({step})):")
             ind += 1
         elif u in ("ENDDO", "END DO"):
             ind -= 1

@@ -140,3 +140,145 @@ def test_lsd_post_processing_matches_reference_statements():
     fsnip.run("rhoofr_utils.mod.F90", 548, 558, env)
     assert abs(env["chrg"].csums - csums) < 1e-12 and abs(env["chrg"].csumsabs - csumsabs) < 1e-12
     assert np.allclose(rhoe.T, want, rtol=0, atol=1e-15)
+
+
+@needs_ref
+def test_kpoint_variants_match_reference_statements():
+    """One k-point of rhoofr_c (rhoofr_c_utils.mod.F90:117-178,182: charge and kinetic sums, the state loop with
+    set_psi_1_state_g_kpts, state_utils.mod.F90:202-222, and build_density_sum) and the k-point unpack of vpsi
+    (vpsi_utils.mod.F90:562-625), executed from the reference's statements, against the oracle."""
+    from oracle import fsnip_cases as fc
+    geo = orc.make_geometry(16)
+    c0, f, hgkp, hgkm, v = orc.synthetic_kpt_inputs(geo, 4, seed=5)
+    f = f.copy()
+    f[1] = 0.0
+    for group, ngroups in ((0, 1), (1, 2)):
+        a = fc.rhoofr_kpt(geo, c0, f, 0.37, hgkp, hgkm, 2.2, 1.1, group, ngroups)
+        b = orc.rhoofr_kpt(geo, c0, f, 0.37, hgkp, hgkm, 2.2, 1.1, group, ngroups)
+        assert relmax(b["rhoe"], a["rhoe"]) < 1e-13
+        assert abs(a["ekin"] - b["ekin"]) < 1e-12 and abs(a["rsum_g"] - b["rsum_g"]) < 1e-12
+        c2a = fc.vpsi_kpt(geo, c0, 0.5 * c0, f, hgkp, hgkm, v, 1.1, group, ngroups)
+        assert relmax(orc.vpsi_kpt(geo, c0, 0.5 * c0, f, hgkp, hgkm, v, 1.1, group, ngroups), c2a) < 1e-13
+
+
+@needs_ref
+@pytest.mark.parametrize("geq0", [True, False])
+def test_ppener_matches_reference_statements(geq0):
+    """ppener_utils.mod.F90:58-104 against the oracle's ppener (both G = 0 branches)."""
+    import dataclasses
+    from oracle import fsnip_cases as fc
+    geo = orc.make_density_geometry((16, 16, 16))
+    rng = np.random.default_rng(3)
+    n = geo.ngw
+    rhog, eivps, eirop = (rng.standard_normal(n) + 1j * rng.standard_normal(n) for _ in range(3))
+    scg = rng.random(n) + 0.1
+    g = dataclasses.replace(geo, geq0=geq0) if dataclasses.is_dataclass(geo) else geo
+    want = orc.ppener(g, rhog, scg, eivps, eirop)
+    got = fc.ppener(g, rhog, scg, eivps, eirop, geq0)
+    for w, h in zip(want[:5], got[:5]):
+        assert abs(w - h) < 1e-11 * max(1.0, abs(w))
+    assert relmax(got[5], want[5]) < 1e-14
+
+
+@needs_ref
+@pytest.mark.parametrize("nsup", [None, 2])
+def test_tau_variants_match_reference_statements(nsup):
+    """tauofr (tauofr_utils.mod.F90:82-102 with dpsisc :121-135 and tauadd :148-173) and vtaupsi
+    (vtaupsi_utils.mod.F90:63-89 with taupot :103-127 and ftauadd :142-163): the reference's state loops executed
+    statement by statement, with and without LSD, against the oracle."""
+    from oracle import fsnip_cases as fc
+    geo = orc.make_geometry(16)
+    c0, f, _ = orc.synthetic_inputs(geo, 5, seed=2, f_pattern="mixed")
+    gk = orc.gk_cartesian(geo)
+    for group, ngroups in ((0, 1), (1, 2)):
+        assert relmax(orc.tauofr(geo, c0, f, gk, 2.0, 1.2, nsup, group, ngroups),
+                      fc.tauofr(geo, c0, f, gk, 2.0, 1.2, nsup, group, ngroups)) < 1e-13
+        vt = np.random.default_rng(1).random((1 if nsup is None else 2, geo.nnr1))
+        assert relmax(orc.vtaupsi(geo, c0, 0.3 * c0, f, gk, vt, 1.2, nsup, group, ngroups),
+                      fc.vtaupsi(geo, c0, 0.3 * c0, f, gk, vt, 1.2, nsup, group, ngroups)) < 1e-13
+
+
+@needs_ref
+def test_exact_exchange_pair_terms_match_reference_statements():
+    """hfxab (hfx_utils.mod.F90:1050-1106, both packings iran = 1, 2) and hfxaa (:1216-1256) against the oracle's
+    _hfx_pair / _hfx_diag."""
+    from oracle import fsnip_cases as fc
+    nr = (16, 16, 16)
+    geo_w, geo_d = orc.make_geometry(nr), orc.make_density_geometry(nr)
+    c0, _, _ = orc.synthetic_inputs(geo_w, 3, seed=2)
+    scgx = orc.hfx_coulomb_kernel(geo_d, 1.1)
+    pa = orc.invfftn_sparse(geo_w, orc.set_psi_2_states_g(geo_w, c0[0], c0[1]))
+    pb = orc.invfftn_sparse(geo_w, orc.set_psi_2_states_g(geo_w, c0[2], c0[1]))
+    for iran in (1, 2):
+        e1, a1, b1 = fc.hfxab(geo_w, geo_d, pa, pb, iran, 0.37, scgx, 2.2)
+        e2, a2, b2 = orc._hfx_pair(geo_w, geo_d, pa, pb, iran, 0.37, scgx, 2.2)
+        assert abs(e1 - e2) < 1e-13 and relmax(a2, a1) < 1e-13 and relmax(b2, b1) < 1e-13
+    e1, a1 = fc.hfxaa(geo_w, geo_d, pa, 0.37, scgx, 2.2)
+    e2, a2 = orc._hfx_diag(geo_w, geo_d, pa, 0.37, scgx, 2.2)
+    assert abs(e1 - e2) < 1e-13 and relmax(a2, a1) < 1e-13
+
+
+@needs_ref
+@pytest.mark.parametrize("nsup", [2, 3])
+def test_lsd_variants_match_reference_statements(nsup):
+    """rhoofr with the spin-resolved accumulation (rhoofr_utils.mod.F90:369-385, build_density_real / _imag) and vpsi
+    with the spin-resolved potential (vpsi_utils.mod.F90:450-482) incl. the pair that straddles the spin boundary."""
+    from oracle import fsnip_cases as fc
+    geo = orc.make_geometry(16)
+    c0, f, _ = orc.synthetic_inputs(geo, 5, seed=2, f_pattern="mixed")
+    v2 = np.random.default_rng(3).random((2, geo.nnr1))
+    part = orc.rhoofr_lsd(geo, c0, f, 2.0, 1.2, nsup, 0, 2)["rhoe"]          # ngroups = 2: the partial channel densities
+    assert relmax(part, fc.rhoofr_lsd(geo, c0, f, 2.0, 1.2, nsup, 0, 2)) < 1e-13
+    assert relmax(orc.vpsi_lsd(geo, c0, 0.3 * c0, f, v2, 1.2, nsup), fc.vpsi_lsd(geo, c0, 0.3 * c0, f, v2, 1.2, nsup)) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The golden vectors the simulator and GPU tests use (tests/golden/, made from the oracle by tools/make_golden.py)
+# reproduced by the reference's statements: links those fixtures to reference code, not only to the restatement.
+# ---------------------------------------------------------------------------------------------------------------
+@needs_ref
+def test_committed_golden_vectors_are_reproduced_by_reference_statements():
+    from helpers import (golden_cases, golden_kpt_cases, golden_lsd_cases, golden_tau_cases, load_golden,
+                         load_golden_kpt, load_golden_lsd, load_golden_tau)
+    from oracle import fsnip_cases as fc
+    for path in golden_cases():
+        d = load_golden(path)
+        geo = _geo(d)
+        assert relmax(fc.rhoofr(geo, d["c0"], d["f"], d["omega"], d["tpiba2"], d["group"], d["ngroups"]), d["rhoe"]) < 1e-13
+        assert relmax(fc.vpsi(geo, d["c0"], d["c2_in"], d["f"], d["vpot"], d["tpiba2"], d["group"], d["ngroups"]),
+                      d["c2_out"]) < 1e-13
+        if d["ngroups"] == 1:
+            ekin, rsum = fc.kin_energy(geo, d["c0"], d["f"], d["tpiba2"])
+            assert abs(ekin - d["ekin"]) < 1e-12 * max(1.0, abs(ekin)) and abs(rsum - d["rsum_g"]) < 1e-12 * max(1.0, rsum)
+    for path in golden_lsd_cases():
+        d = load_golden_lsd(path)
+        geo = _geo(d)
+        part = fc.rhoofr_lsd(geo, d["c0"], d["f"], d["omega"], d["tpiba2"], d["nsup"])
+        part[0] += part[1]                                               # alpha+beta / beta (:543-559, pinned separately)
+        assert relmax(part, d["rhoe"]) < 1e-13
+        assert relmax(fc.vpsi_lsd(geo, d["c0"], d["c2_in"], d["f"], d["vpot"], d["tpiba2"], d["nsup"]), d["c2_out"]) < 1e-13
+    for path in golden_kpt_cases():
+        d = load_golden_kpt(path)
+        geo = _geo(d)
+        r = fc.rhoofr_kpt(geo, d["c0"], d["f"], d["wk"], d["hgkp"], d["hgkm"], d["omega"], d["tpiba2"])
+        assert relmax(r["rhoe"], d["rhoe"]) < 1e-13 and abs(r["ekin"] - d["ekin"]) < 1e-12 and abs(r["rsum_g"] - d["rsum_g"]) < 1e-12
+        assert relmax(fc.vpsi_kpt(geo, d["c0"], d["c2_in"], d["f"], d["hgkp"], d["hgkm"], d["vpot"], d["tpiba2"]),
+                      d["c2_out"]) < 1e-13
+    for path in golden_tau_cases():
+        d = load_golden_tau(path)
+        geo = _geo(d)
+        nsup = None if d["nsup"] < 0 else d["nsup"]
+        assert relmax(fc.tauofr(geo, d["c0"], d["f"], d["gk"], d["omega"], d["tpiba2"], nsup), d["tau"]) < 1e-13
+        assert relmax(fc.vtaupsi(geo, d["c0"], d["c2_in"], d["f"], d["gk"], d["vtau"], d["tpiba2"], nsup), d["c2_out"]) < 1e-13
+
+
+@needs_ref
+def test_vofrho_golden_vectors_are_reproduced_by_reference_ppener():
+    from helpers import ener_vector, golden_vofrho_cases, load_golden_vofrho
+    from oracle import fsnip_cases as fc
+    for path in golden_vofrho_cases():
+        d = load_golden_vofrho(path)
+        eh, ei, ee, eps, vploc, vtemp = fc.ppener(None, d["rhog"], d["scg"], d["eivps"], d["eirop"], geq0=True)
+        assert relmax(vtemp, d["vtemp"]) < 1e-13
+        got = ener_vector(dict(eh=complex(eh), ei=complex(ei), ee=complex(ee), eps=complex(eps), vploc=float(vploc)))
+        assert np.abs(got - d["ener"]).max() < 1e-11 * max(1.0, np.abs(d["ener"]).max())
