@@ -1,6 +1,6 @@
 """The reference's own Fortran statements (executed by oracle/fsnip.py) assembled into the non-transform parts of
 ``rhoofr`` and ``vpsi``: pairing loops, occupation rules, +-G unpack with the kinetic term, density accumulation,
-``kin_energy`` / ``dotp``.  The transforms between them (``set_psi_*``, ``invfftn``, ``fwfftn``) come from the oracle:
+``kin_energy`` / ``dotp``, ``set_psi_*``.  The transforms between them (``invfftn``, ``fwfftn``) come from the oracle:
 those are pinned by the reference's helper kernels in oracle/_ref (tests/test_oracle_ref.py).  TEST INFRASTRUCTURE:
 used by tests/test_fsnip_pin.py and tools/make_golden_fsnip.py only."""
 from __future__ import annotations
@@ -10,6 +10,21 @@ import numpy as np
 from oracle import cpmd_oracle as orc
 from oracle import fsnip
 from oracle.fsnip import FArr, ns
+
+
+def set_psi(geo, c1, c2=None):
+    """Ray storage psi of one state (c2 None: set_psi_1_state_g with alpha = 1, state_utils.mod.F90:142-166) or of a
+    packed pair (set_psi_2_states_g, :183-187), from the reference's statements."""
+    psi = np.zeros(geo.kr[0] * geo.nrays, complex)
+    env = dict(jgw=geo.ngw, psi=FArr(psi), nzfs=FArr(geo.nzhs), inzs=FArr(geo.indzs), geq0=bool(geo.geq0), c1=FArr(c1),
+               uimag=1j)
+    if c2 is None:
+        env.update(alpha=1.0 + 0.0j, zone=1.0 + 0.0j)
+        fsnip.run("state_utils.mod.F90", 142, 166, env)
+    else:
+        env.update(c2=FArr(c2))
+        fsnip.run("state_utils.mod.F90", 183, 187, env)
+    return psi
 
 
 def part_1d_functions():
@@ -68,10 +83,7 @@ def rhoofr(geo, c0, f, omega, tpiba2, group=0, ngroups=1):
     for is1, is2 in pair_loop("rhoofr", nstate, group, ngroups):
         if f[is1 - 1] == 0.0 and (is2 > nstate or f[is2 - 1] == 0.0):
             continue                                                       # tfcal, rhoofr_utils.mod.F90:312-316
-        if is2 > nstate:
-            psi = orc.set_psi_1_state_g(geo, c0[is1 - 1])
-        else:
-            psi = orc.set_psi_2_states_g(geo, c0[is1 - 1], c0[is2 - 1])
+        psi = set_psi(geo, c0[is1 - 1], None if is2 > nstate else c0[is2 - 1])
         psi = orc.invfftn_sparse(geo, psi)
         env = dict(crge=ns(f=fa), parm=ns(omega=omega), is1=is1, is2=is2, nstate=nstate)
         fsnip.run("rhoofr_utils.mod.F90", 369, 374, env)
@@ -87,10 +99,7 @@ def vpsi(geo, c0, c2, f, vpot, tpiba2, group=0, ngroups=1, tksham=False):
     c2v = np.zeros((geo.ngw, nstate), complex)                             # column-major C2_vpsi(ngw, nstate)
     c0f = FArr(np.ascontiguousarray(c0.T))
     for is1, is2 in pair_loop("vpsi", nstate, group, ngroups):
-        if is2 > nstate:
-            psi = orc.set_psi_1_state_g(geo, c0[is1 - 1])
-        else:
-            psi = orc.set_psi_2_states_g(geo, c0[is1 - 1], c0[is2 - 1])
+        psi = set_psi(geo, c0[is1 - 1], None if is2 > nstate else c0[is2 - 1])
         psi = orc.fwfftn_sparse(geo, vpot * orc.invfftn_sparse(geo, psi))
         env = dict(f=FArr(np.asarray(f, float)), is1=is1, is2=is2, nostat=nstate, cntl=ns(tksham=bool(tksham)),
                    prcp_com=ns(akin=0.0, gskin=1.0, gckin=0.0, gakin=0.0), psi_p=FArr(psi), nzhs=FArr(geo.nzhs),
@@ -320,10 +329,7 @@ def rhoofr_lsd(geo, c0, f, omega, tpiba2, nsup, group=0, ngroups=1):
     for is1, is2 in pair_loop("rhoofr", nstate, group, ngroups):
         if f[is1 - 1] == 0.0 and (is2 > nstate or f[is2 - 1] == 0.0):
             continue
-        if is2 > nstate:
-            psi = orc.set_psi_1_state_g(geo, c0[is1 - 1])
-        else:
-            psi = orc.set_psi_2_states_g(geo, c0[is1 - 1], c0[is2 - 1])
+        psi = set_psi(geo, c0[is1 - 1], None if is2 > nstate else c0[is2 - 1])
         psi = orc.invfftn_sparse(geo, psi)
         env = dict(crge=ns(f=fa), parm=ns(omega=omega), is1=is1, is2=is2, nstate=nstate, cntl=ns(tlsd=True),
                    spin_mod=ns(nsup=nsup), psi_p=FArr(psi), rhoe_p=FArr(rho), llr1=geo.nnr1,
@@ -341,10 +347,7 @@ def vpsi_lsd(geo, c0, c2, f, vpot2, tpiba2, nsup, group=0, ngroups=1, tksham=Fal
     vdg = np.asfortranarray(np.asarray(vpot2).T)                             # vpotdg(nnr1, 2)
     vx = vdg.reshape(-1, order="F")                                          # vpotx: the same storage, 1-D
     for is1, is2 in pair_loop("vpsi", nstate, group, ngroups):
-        if is2 > nstate:
-            psi = orc.set_psi_1_state_g(geo, c0[is1 - 1])
-        else:
-            psi = orc.set_psi_2_states_g(geo, c0[is1 - 1], c0[is2 - 1])
+        psi = set_psi(geo, c0[is1 - 1], None if is2 > nstate else c0[is2 - 1])
         psi = orc.invfftn_sparse(geo, psi)
         envp = dict(cntl=ns(tlsd=True), ispin=2, is1=is1, spin_mod=ns(nsup=nsup), td_prop=ns(td_extpot=False),
                     nnrx=geo.nnr1, psi_p=FArr(psi), vpotx=FArr(vx), leadx=geo.nnr1, uimag=1j, vpotdg=FArr(vdg))
