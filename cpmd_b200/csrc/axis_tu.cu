@@ -154,10 +154,15 @@ void y_inv(cudaStream_t st, const cplx* T1, cplx* T2, const PlanDev& pd, int npa
 
 template <bool HALF>
 void y_fwd_t(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg) {
-  auto k = k_y_fwd<R1, R2, B, HALF>;
-  allow_smem(k, kSmemYZ2);
+  // two exchange buffers (+ the private cp.async slots of the next pair's rows, R2 elements per thread, where
+  // they do not cost a resident block)
+  constexpr size_t slots = (size_t)R2 * B * RM * sizeof(cplx);
+  constexpr bool async = CPB_YFWD_ASYNC && (YZBlocks<R1, R2>::v * (kSmemYZ2 + slots + 1024) <= (size_t)228 * 1024);
+  auto k = k_y_fwd<R1, R2, B, HALF, async>;
+  const size_t smem = kSmemYZ2 + (async ? slots : 0);
+  allow_smem(k, smem);
   CPB_LAUNCH_PDL(4, k, CPB_Y_ZFAST ? dim3(pd.nzb, nxc, (npair + ppg - 1) / ppg) : dim3(nxc, pd.nzb, (npair + ppg - 1) / ppg),
-             dim3(B * RM), kSmemYZ2, st, T2, T1, pd, xt0, npair, ppg);
+             dim3(B * RM), smem, st, T2, T1, pd, xt0, npair, ppg);
 }
 void y_fwd(cudaStream_t st, const cplx* T2, cplx* T1, const PlanDev& pd, int npair, int xt0, int nxc, int ppg,
            bool half) {

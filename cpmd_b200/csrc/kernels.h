@@ -856,6 +856,9 @@ constexpr int kStages = 2;
 #ifndef CPB_ZRHO_XB
 #define CPB_ZRHO_XB 2
 #endif
+#ifndef CPB_YFWD_ASYNC
+#define CPB_YFWD_ASYNC 1  // k_y_fwd: next pair's rows by cp.async into private slots (0: register prefetch)
+#endif
 #ifndef CPB_YINV_XB
 #define CPB_YINV_XB 2
 #endif
@@ -981,7 +984,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, (YZBlocksX<R1, R2, XB>::v))
 }
 
 // y pass, forward: reads all n2 rows of the chunk's T2, writes only the rays of the plane into T1.
-template <int R1, int R2, int B, bool HALF>
+// ASYNC: the next pair's rows travel by cp.async into private shared-memory slots instead of registers
+template <int R1, int R2, int B, bool HALF, bool ASYNC>
 CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     k_y_fwd(const cplx* CPB_RESTRICT T2, cplx* CPB_RESTRICT T1, PlanDev pd, int xt0, int npair, int ppg) {
   constexpr int N = R1 * R2;
@@ -1008,13 +1012,19 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
   pdl_wait();  // T2 comes from the preceding kernel
   const cplx* src = T2 + ((size_t)xtc * N * pd.nzb + zr) * B + b;
   cplx* dst = T1 + ((size_t)(xt0 + xtc) * pd.nrays + pd.rayoff[zr]) * B + b;
-  cplx nv[R2];
+  // ASYNC: the rows of the NEXT pair travel with 16-byte cp.async copies into private shared-memory slots (a warp
+  // instruction = 4 whole 128-byte rows): no registers are held by loads in flight
+  cplx* NV = S + 2 * (N * B);  // [R2][threads]
+  constexpr int nthr = B * MaxOf<R1, R2>::v;
+  cplx nv[ASYNC ? 1 : R2];
   auto fetch = [&](int pair) {
     const cplx* s = src + (size_t)pair * t2_pair;
     static_for<0, R2>([&](auto kk) {
       constexpr int k = decltype(kk)::value;
-      nv[k] = s[(size_t)(r + R1 * k) * ystride];
+      if constexpr (ASYNC) cp_async16(&NV[k * nthr + tid], &s[(size_t)(r + R1 * k) * ystride]);
+      else nv[k] = s[(size_t)(r + R1 * k) * ystride];
     });
+    if constexpr (ASYNC) cp_async_commit();
   };
   if (r < R1 && p0 < p1) fetch(p0);
   int buf = 0;
@@ -1022,9 +1032,16 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS(B* MaxOf<R1, R2>::v, YZBlocks<R1, R2>::v)
     cplx* Sb = S + buf * (N * B) + b;
     if (r < R1) {
       cplx v[R2];
-      static_for<0, R2>([&](auto kk) { v[decltype(kk)::value] = nv[decltype(kk)::value]; });
-      pass_a<R2, R1, false>(v, r, pd.tw2, Sb, B);
-      if (pair + 1 < p1) fetch(pair + 1);
+      if constexpr (ASYNC) {
+        cp_async_wait_all();
+        static_for<0, R2>([&](auto kk) { v[decltype(kk)::value] = NV[decltype(kk)::value * nthr + tid]; });
+        if (pair + 1 < p1) fetch(pair + 1);  // my slots are free again
+        pass_a<R2, R1, false>(v, r, pd.tw2, Sb, B);
+      } else {
+        static_for<0, R2>([&](auto kk) { v[decltype(kk)::value] = nv[decltype(kk)::value]; });
+        pass_a<R2, R1, false>(v, r, pd.tw2, Sb, B);
+        if (pair + 1 < p1) fetch(pair + 1);
+      }
     }
     __syncthreads();
     if (r < R2) {
