@@ -166,7 +166,11 @@ struct cpb_plan {
   static constexpr int kNumWS = 2;
   WorkSpace ws[kNumWS];
   rt::event_t vpot_event = nullptr;  // one-shot: the next vpsi waits for it before its first z pass
-  int nws = 1;  // work spaces in use (default 1: on B200 the overlap costs vpsi more than it gains; CPB_STREAMS=2)
+  // work spaces in use.  Two: consecutive batches alternate between two streams, so the tail of one batch's
+  // kernels (last, partly filled wave; FP64-bound z pass) runs beside the head of the next batch (gather-bound x
+  // pass): 192^3 29.3 -> 28.5 ms, 256^3 9.64 -> 9.47 ms per step (profiles/r03j/r03k_probe_streams.txt).  With the
+  // round-1 kernels the overlap cost vpsi more than it gained; CPB_STREAMS=1 serialises the batches again.
+  int nws = 2;
   rt::event_t ev_fork = nullptr;
   size_t workspace_bytes = 0;
   // per-call pair descriptors

@@ -391,8 +391,8 @@ enum {
 };
 int cpb_plan_set_profiling(cpb_plan* plan, int on);
 /* Batches of a call alternate between `n` work spaces/streams, 1 <= n <= the number allocated at
- * plan creation (env CPB_STREAMS, default 1 = all kernels serialised on one stream; 2 overlaps the
- * HBM-bound kernels of one batch with the FP64-bound z kernel of the other). */
+ * plan creation (env CPB_STREAMS, default 2: the tail of one batch's kernels runs beside the head of the next
+ * batch's; 1 = all kernels serialised on one stream).  Results are bit-identical either way. */
 int cpb_plan_set_streams(cpb_plan* plan, int n);
 int cpb_plan_get_kernel_times(cpb_plan* plan, double* ms /*[CPB_NKINDS]*/, long* counts /*[CPB_NKINDS]*/,
                               int reset);

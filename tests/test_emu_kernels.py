@@ -274,12 +274,13 @@ def test_context_mirrors_reference_signatures(emu_cdll):
 
 
 def test_two_work_spaces(emu_cdll, monkeypatch):
-    """CPB_STREAMS=2: consecutive batches alternate between two work spaces / streams; results are
-    bit-identical to the single-stream run (rho is still accumulated batch after batch in order)."""
+    """Two work spaces / streams (the default): consecutive batches alternate between them; results are
+    bit-identical to the single-stream run, CPB_STREAMS=1 (rho is still accumulated batch after batch in order)."""
     d = synthetic.make_inputs(20, 9, f_pattern="mixed")
+    monkeypatch.setenv("CPB_STREAMS", "1")
     p1 = _plan(d, emu_cdll, max_batch=2)
     assert p1.info["streams"] == 1
-    monkeypatch.setenv("CPB_STREAMS", "2")
+    monkeypatch.delenv("CPB_STREAMS")
     p2 = _plan(d, emu_cdll, max_batch=2)
     assert p2.info["streams"] == 2
     r1, *s1 = p1.rhoofr(d["c0"], d["f"])

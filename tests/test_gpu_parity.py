@@ -192,13 +192,14 @@ def test_full_size_properties(dev):
 
 
 def test_two_streams_bit_identical(dev, monkeypatch):
-    """CPB_STREAMS=2 (batches alternate between two work-space streams) against the default."""
+    """Two work-space streams (the default: batches alternate between them) against CPB_STREAMS=1."""
     n, ns = 48, 13
     d = synthetic.make_inputs(n, ns, f_pattern="mixed")
+    monkeypatch.setenv("CPB_STREAMS", "1")
     p1 = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
-    monkeypatch.setenv("CPB_STREAMS", "2")
+    monkeypatch.delenv("CPB_STREAMS")
     p2 = Plan(d["nr"], d["inyh"], d["hg"], max_batch=2)
-    assert p2.info["streams"] == 2
+    assert p1.info["streams"] == 1 and p2.info["streams"] == 2
     r1, s1, c1 = _dev_run(p1, d, dev)
     r2, s2, c2 = _dev_run(p2, d, dev)
     assert np.array_equal(r1, r2) and s1 == s2 and np.array_equal(c1, c2)
