@@ -126,7 +126,8 @@ struct cpb_plan {
   const void* psi_key_ptr = nullptr;
   long psi_key[5] = {0, 0, 0, 0, 0};  // ld, nstate, ngroups, my_group, nsup
   double prologue_pairs = 0.25;  // block prologue cost in pair-times (pairs_per_group model)
-  double prologue_pairs_x = 1.0; // same for the mirror-pair x kernels (position tables + hg per block; CPB_PROLOGUE_X)
+  double prologue_pairs_x = 1.0; // same for the mirror-pair forward x kernel (position tables + hg per block; CPB_PROLOGUE_X)
+  double prologue_pairs_xinv = 1.0;  // ... and for the inverse one (CPB_PROLOGUE_XINV; CPB_PROLOGUE_X sets both)
   int x_sub = 32;         // pairs per forward x-pass sub-batch (measured: fewer launches beat L2 residency of G, profiles/r01g_notes.txt)
   size_t t1_pair = 0;     // elements of T1 per pair
   size_t g_pair = 0;      // elements of the band-ray storage per pair (nxb * nrp)
@@ -163,7 +164,7 @@ struct cpb_plan {
     cudaStream_t s = nullptr;
     rt::event_t ev_join = nullptr, ev_rho = nullptr;
   };
-  static constexpr int kNumWS = 2;
+  static constexpr int kNumWS = 4;
   WorkSpace ws[kNumWS];
   rt::event_t vpot_event = nullptr;  // one-shot: the next vpsi waits for it before its first z pass
   // work spaces in use.  Two: consecutive batches alternate between two streams, so the tail of one batch's
@@ -461,7 +462,7 @@ void run_x_inv(cpb_plan* p, cpb_plan::WorkSpace& w, const cplx* c0, long ldc, co
   if (p->mirror && !p->kpt_mode) {
     double* kin = p->kin_cur ? p->kin_cur + (size_t)off * p->nbx_m * 4 : nullptr;
     p->kx->x_inv_m(st, c0, ldc, w.T1, p->pd, prb, nb,
-                   pairs_per_group(p, nb, p->nbx_m, p->kx->x_inv_m_blocks, p->prologue_pairs_x), p->half_x, kin, p->geq0);
+                   pairs_per_group(p, nb, p->nbx_m, p->kx->x_inv_m_blocks, p->prologue_pairs_xinv), p->half_x, kin, p->geq0);
     return;
   }
   p->kx->x_inv(st, c0, ldc, w.T1, p->kpt_mode ? p->pdk : p->pd, prb, nb,
@@ -1031,7 +1032,8 @@ int cpb_plan_create(cpb_plan** out, const int* nr, const int* kr, int ngw, const
     p->t1_pair = (size_t)p->nxt * nrays * Bx;
     if (const char* e = std::getenv("CPB_X_SUB")) p->x_sub = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("CPB_PROLOGUE")) p->prologue_pairs = std::max(0.0, std::atof(e));
-    if (const char* e = std::getenv("CPB_PROLOGUE_X")) p->prologue_pairs_x = std::max(0.0, std::atof(e));
+    if (const char* e = std::getenv("CPB_PROLOGUE_X")) p->prologue_pairs_x = p->prologue_pairs_xinv = std::max(0.0, std::atof(e));
+    if (const char* e = std::getenv("CPB_PROLOGUE_XINV")) p->prologue_pairs_xinv = std::max(0.0, std::atof(e));
     p->g_pair = (size_t)nxb * nrp;
     p->t2_pair = (size_t)p->nxt * n2 * nzb * Bx;
     if (p->auto_batch) {
