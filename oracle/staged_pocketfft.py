@@ -68,7 +68,8 @@ _MAPS = {}
 
 def _maps(geo):
     key = id(geo)
-    m = _MAPS.get(key)
+    hit = _MAPS.get(key)
+    m = hit[1] if hit is not None and hit[0] is geo else None   # id() alone is reused after garbage collection
     if m is None:
         n1, n2, n3 = geo.nr
         kr1, kr2 = geo.kr[0], geo.kr[1]
@@ -80,7 +81,7 @@ def _maps(geo):
         ms = np.ascontiguousarray(geo.msp2.astype(np.int64) - 1)  # ray -> y + (z - kr3min) * kr2s
         m = (n1, n2, n3, kr2, nzb, nzc, izc, ms)
         _MAPS.clear()
-        _MAPS[key] = m
+        _MAPS[key] = (geo, m)      # holds the geometry: its id cannot be handed to another object meanwhile
     return m
 
 
