@@ -184,11 +184,25 @@ inline void cp_async16(void* dst, const void* src) {
   char* d = static_cast<char*>(dst);
   for (int i = 0; i < 16; ++i) d[i] = s[i];
 }
+inline uint64_t l2_keep_policy() { return 0; }
+inline void cp_async16_keep(void* dst, const void* src, uint64_t) { cp_async16(dst, src); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 #else
 CPB_D void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the same copy with an L2 evict-last policy: the plane-wave columns are gathered as 16-byte halves of 32-byte
+// sectors whose other half belongs to a different ray (another block); the sector should survive in L2 until
+// that block asks for it while the streaming intermediates pass through
+CPB_D uint64_t l2_keep_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+CPB_D void cp_async16_keep(void* dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol)
+               : "memory");
 }
 CPB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 CPB_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

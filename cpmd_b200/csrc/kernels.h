@@ -447,6 +447,17 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XCfg<R1, R2, SL>::MINB_FWD
 // The centre ray (odd nrays) is its own mirror: its mirror slot is switched off and its -G positions
 // read the ray's own slots.
 // ---------------------------------------------------------------------------------------------
+// gathers of the mirror-pair kernels: cp.async with an L2 evict-last hint (CPB_GATHER_KEEP=1) or plain
+#ifndef CPB_GATHER_KEEP
+#define CPB_GATHER_KEEP 0
+#endif
+#if CPB_GATHER_KEEP
+#define CPB_GATHER_POLICY const uint64_t gather_pol = l2_keep_policy()
+#define CPB_GATHER16(dst, src) cp_async16_keep(dst, src, gather_pol)
+#else
+#define CPB_GATHER_POLICY
+#define CPB_GATHER16(dst, src) cp_async16(dst, src)
+#endif
 template <int R1, int R2, int SL, bool HALF>
 struct XMCfg {
   using C = XCfg<R1, R2, SL>;
@@ -501,6 +512,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   double* RED2 = RED + 4 * NA;                           // [2][4][8], alternating per pair
   int* PS1 = reinterpret_cast<int*>(RED2 + 2 * 4 * 8);   // the block's pair descriptors [kMaxGroup] each
   int* PS2 = PS1 + kMaxGroup;
+  CPB_GATHER_POLICY;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
@@ -548,8 +560,8 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
       constexpr int k = decltype(kk)::value;
       constexpr int j = k - KR::lo;
       if (tab[j] != kNoPW && !(tab[j] & kNegPW)) {
-        cp_async16(&st[(0 * NPOS + (k - C0)) * NA + tidA], c1p + tab[j]);
-        if (s2 >= 0) cp_async16(&st[(1 * NPOS + (k - C0)) * NA + tidA], c2p + tab[j]);
+        CPB_GATHER16(&st[(0 * NPOS + (k - C0)) * NA + tidA], c1p + tab[j]);
+        if (s2 >= 0) CPB_GATHER16(&st[(1 * NPOS + (k - C0)) * NA + tidA], c2p + tab[j]);
       }
     });
     cp_async_commit();
@@ -675,6 +687,7 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
   double* PCB = PCA + kMaxGroup;
   int* PS1 = reinterpret_cast<int*>(PCB + kMaxGroup);
   int* PS2 = PS1 + kMaxGroup;
+  CPB_GATHER_POLICY;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.y * ppg;
   const int p1 = (p0 + ppg < npair) ? p0 + ppg : npair;
@@ -749,11 +762,11 @@ CPB_GLOBAL CPB_LAUNCH_BOUNDS((XCfg<R1, R2, SL>::NT), (XMCfg<R1, R2, SL, HALF>::M
 #else
           const uint32_t ig = tab[j];
 #endif
-          cp_async16(&CS[0 * NPOS * NA + o], a1 + ig);
-          if (s2 >= 0) cp_async16(&CS[1 * NPOS * NA + o], a2 + ig);
+          CPB_GATHER16(&CS[0 * NPOS * NA + o], a1 + ig);
+          if (s2 >= 0) CPB_GATHER16(&CS[1 * NPOS * NA + o], a2 + ig);
           if constexpr (ACC) {
-            cp_async16(&CS[2 * NPOS * NA + o], o1 + ig);
-            if (s2 >= 0) cp_async16(&CS[3 * NPOS * NA + o], o2 + ig);
+            CPB_GATHER16(&CS[2 * NPOS * NA + o], o1 + ig);
+            if (s2 >= 0) CPB_GATHER16(&CS[3 * NPOS * NA + o], o2 + ig);
           }
         }
       });
