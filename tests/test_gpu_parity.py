@@ -673,6 +673,58 @@ def test_c0_upload_and_charge_check(dev):
     assert abs(rg_p - rr_p) > 1e-6
 
 
+def test_empty_and_degenerate_inputs_gpu(dev):
+    """Ragged / empty inputs the reference loops handle implicitly (rhoofr_utils.mod.F90:306-316,
+    vpsi_utils.mod.F90:376-383, part_1d.mod.F90:22-57), on the GPU through the host- and the device-pointer
+    entry points: one state, no state, a group that owns no state, nothing occupied, a padded leading
+    dimension (ld > ngw) whose pad rows must stay untouched."""
+    geo = orc.make_geometry(16)
+    p = Plan(geo.nr, geo.inyh, geo.hg, max_batch=2)
+    c0, f, v = orc.synthetic_inputs(geo, 1)
+    ref = orc.rhoofr(geo, c0, f, 1.0, 1.0)
+    c2_ref = orc.vpsi(geo, c0, np.zeros_like(c0), f, v, 1.0)
+    # one state (single-state path only), host pointers and device pointers
+    rho, ek, rg, rr = p.rhoofr(c0, f)
+    assert relmax(rho, ref["rhoe"]) < RTOL and abs(ek - ref["ekin"]) < ETOL and abs(rg - rr) < ETOL
+    c2 = np.zeros_like(c0)
+    p.vpsi(c0, c2, f, v)
+    assert relmax(c2, c2_ref) < RTOL
+    c0d, vd = torch.from_numpy(c0).to(dev), torch.from_numpy(v).to(dev)
+    rhod = torch.full((p.nnr1,), 3.0, dtype=torch.float64, device=dev)
+    ekd, rgd, rrd = p.rhoofr_dev(c0d, f, rhod)
+    assert np.array_equal(rhod.cpu().numpy(), rho) and (ekd, rgd, rrd) == (ek, rg, rr)
+    # no state at all: rho is zeroed, scalars vanish, vpsi is a no-op
+    c00 = np.zeros((0, geo.ngw), complex)
+    rho0, ek0, rg0, rr0 = p.rhoofr(c00, np.zeros(0))
+    assert not rho0.any() and (ek0, rg0, rr0) == (0.0, 0.0, 0.0)
+    p.vpsi(c00, np.zeros_like(c00), np.zeros(0), v)
+    # a group that owns no state (more groups than states)
+    rho0, ek0, rg0, rr0 = p.rhoofr(c0, f, ngroups=3, my_group=2)
+    assert not rho0.any() and (ek0, rg0, rr0) == (0.0, 0.0, 0.0)
+    ekd, rgd, rrd = p.rhoofr_dev(c0d, f, rhod, ngroups=3, my_group=2)
+    assert not rhod.any().item() and (ekd, rgd, rrd) == (0.0, 0.0, 0.0)
+    ones = np.ones_like(c0)
+    p.vpsi(c0, ones, f, v, ngroups=3, my_group=2)
+    assert np.all(ones == 1.0)
+    # nothing occupied: rhoofr skips the pair, vpsi still acts with fi = 1 (vpsi_utils.mod.F90:627-633)
+    rho0, ek0, rg0, rr0 = p.rhoofr(c0, np.zeros(1))
+    assert not rho0.any() and (ek0, rg0, rr0) == (0.0, 0.0, 0.0)
+    c2 = np.zeros_like(c0)
+    p.vpsi(c0, c2, np.zeros(1), v)
+    assert relmax(c2, orc.vpsi(geo, c0, np.zeros_like(c0), np.zeros(1), v, 1.0)) < RTOL
+    # three states in columns of a padded array (ld = ngw + 5): pad rows of c2 keep their values
+    c3, f3, v3 = orc.synthetic_inputs(geo, 3, f_pattern="mixed")
+    ld = geo.ngw + 5
+    c3p = np.zeros((3, ld), complex)
+    c3p[:, :geo.ngw] = c3
+    c2p = np.full((3, ld), 0.25 - 0.5j)
+    want = orc.vpsi(geo, c3, c2p[:, :geo.ngw].copy(), f3, v3, 1.0)
+    rho3, *_ = p.rhoofr(c3p, f3)
+    p.vpsi(c3p, c2p, f3, v3)
+    assert relmax(rho3, orc.rhoofr(geo, c3, f3, 1.0, 1.0)["rhoe"]) < RTOL
+    assert relmax(c2p[:, :geo.ngw], want) < RTOL and np.all(c2p[:, geo.ngw:] == 0.25 - 0.5j)
+
+
 @pytest.mark.parametrize("nr,ns", [(16, 5), ((16, 20, 24), 4), (48, 6), (96, 5)])
 def test_hfx_device_matches_oracle(dev, nr, ns):
     """cpb_hfx_dev (hfx_old, Gamma point, no LSD, no screening: hfx_utils.mod.F90:80-965) against the oracle."""
