@@ -1234,7 +1234,8 @@ static int rhoofr_dev_impl(cpb_plan* p, const void* c0_dev, long ld_c0, int nsta
     double* d_sums = p->d_red + kRedPerState * nblk;
     if (lsd) launch_lsd_sums(p, rhoe_dev, rhoe_dev + nnr1, nnr1, d_sums, ngroups == 1, st);  // :543-559
     else launch_sum(p, rhoe_dev, nnr1, d_sums, st);                                            // :607-619
-    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + 3 * kSumBlocks) * sizeof(double), st);
+    // only what the kernels above wrote travels (LSD: three sums per block, otherwise one)
+    rt::d2h(p->h_red, p->d_red, (size_t)(kRedPerState * nblk + (lsd ? 3 : 1) * kSumBlocks) * sizeof(double), st);
     if ((flags & CPB_ASYNC) && !p->profiling) {
       // enqueue-only: the partial sums are on their way to h_red; cpb_rhoofr_finish waits for them
       cpb_plan::PendingRho& pr = p->pending_rho;
